@@ -1,0 +1,634 @@
+// api.cu -- libcalipso_b200.so: kernels (one CTA per problem instance) + the C ABI of include/calipso_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see calipso_b200/build.py).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/calipso_b200.h"
+#include "device_newton.h"
+#include "host_setup.h"
+
+using namespace cb200;
+
+static_assert(sizeof(cb200_options) == sizeof(Options), "cb200_options must mirror cb200::Options");
+static_assert((int)CB200_S_COUNT == (int)S_COUNT && (int)CB200_I_COUNT == (int)I_COUNT, "slot enums out of sync");
+
+// ---------------------------------------------------------------------------------------------------- batch view
+struct Batch {
+    int count, F;
+    long long ksize;
+    double *w, *cand, *step, *res, *err, *corr, *tmp;
+    double *grad, *gyx, *hzx, *g, *h, *Wv, *Gv, *Cv, *prod, *bgrad, *lambda;
+    double *panels, *D, *Dinv, *xs, *rs, *xp, *mgrad, *q, *g0, *h0, *filter, *krylov, *scal;
+    double *Aval, *rhs;
+    int *istat;
+    __device__ __forceinline__ Inst inst(const DevProblem &P, int b) const
+    {
+        Inst I;
+        const long long t = P.total, n = P.n, m = P.m, p = P.p, N = P.N;
+        I.w = w + b * t; I.cand = cand + b * t; I.step = step + b * t; I.res = res + b * t; I.err = err + b * t;
+        I.corr = corr + b * t; I.tmp = tmp + b * t;
+        I.grad = grad + b * n; I.gyx = gyx + b * n; I.hzx = hzx + b * n;
+        I.g = g + b * m; I.h = h + b * p;
+        I.Wv = Wv + b * (long long)P.nnzW; I.Gv = Gv + b * (long long)P.nnzG; I.Cv = Cv + b * (long long)P.nnzC;
+        I.prod = prod + b * p; I.bgrad = bgrad + b * p; I.lambda = lambda + b * m;
+        I.panels = panels + b * P.panel_total; I.D = D + b * N; I.Dinv = Dinv + b * N;
+        I.xs = xs + b * N; I.rs = rs + b * N; I.xp = xp + b * N; I.mgrad = mgrad + b * N;
+        I.q = q + b * n; I.g0 = g0 + b * m; I.h0 = h0 + b * p;
+        I.filter = filter + b * 4LL * F;
+        I.krylov = krylov ? krylov + b * ksize : nullptr;
+        I.scal = scal + b * (long long)S_COUNT;
+        I.istat = istat + b * (long long)I_COUNT;
+        return I;
+    }
+};
+
+#define CB_THREADS 256
+#define KERNEL_PROLOGUE                                   \
+    __shared__ double red[34];                            \
+    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red};   \
+    const int b = blockIdx.x;                             \
+    if (b >= B.count) return;                             \
+    Inst I = B.inst(P, b);
+
+__global__ void __launch_bounds__(CB_THREADS) k_cone(DevProblem P, Batch B, int flags, int at_candidate)
+{
+    KERNEL_PROLOGUE
+    cone_eval(ctx, P, I, at_candidate ? I.cand : I.w, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1);
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_residual(DevProblem P, Batch B)
+{
+    KERNEL_PROLOGUE
+    residual_eval(ctx, P, I);
+    double th = constraint_violation(ctx, P, I, I.w);
+    if (ctx.tid == 0) I.scal[S_THETA] = th;
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_search_direction(DevProblem P, Batch B, Options o)
+{
+    KERNEL_PROLOGUE
+    int st = search_direction(ctx, P, I, o);
+    if (ctx.tid == 0) I.istat[I_STATUS] = st;
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_cone_search(DevProblem P, Batch B, Options o)
+{
+    KERNEL_PROLOGUE
+    int st = cone_search(ctx, P, I, o);
+    // candidate x, r with the cone step size (solve.jl:224-229)
+    double a = I.scal[S_STEP_SIZE];
+    PAR_FOR(i, P.n + P.m) I.cand[i] = I.w[i] - a * I.step[i];
+    if (ctx.tid == 0 && st != ST_OK) I.istat[I_STATUS] = st;
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_apply_step(DevProblem P, Batch B)
+{
+    KERNEL_PROLOGUE
+    const int n = P.n, m = P.m, p = P.p, N = P.N;
+    const double a = I.scal[S_STEP_SIZE];
+    double *w = I.w, *c = I.cand;
+    // candidate primals for the (possibly reduced) step size, then the update of solve.jl:309-326
+    PAR_FOR(i, N) w[i] = w[i] - a * I.step[i];
+    PAR_FOR(i, m + p) w[N + i] = w[N + i] - a * I.step[N + i];
+    PAR_FOR(i, p) w[N + m + p + i] = c[N + m + p + i];
+    ctx.sync();
+    cone_eval(ctx, P, I, w, 0, 0, 1);
+    double ev = scope_max(ctx, m, [&](int i) { return fabs(I.g[i]); });
+    double cv = scope_max(ctx, p, [&](int i) { return fabs(I.prod[i]); });
+    if (ctx.tid == 0) { I.scal[S_EQUALITY_VIOLATION] = ev; I.scal[S_CONE_PRODUCT_VIOLATION] = cv; }
+    (void)n;
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_jtimes(DevProblem P, Batch B)
+{   // tmp <- J * err  (err used as the input vector)
+    KERNEL_PROLOGUE
+    jacobian_times(ctx, P, I, I.err, I.tmp);
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_lq_evaluate(DevProblem P, Batch B, int flags, int at_candidate)
+{
+    KERNEL_PROLOGUE
+    lq_evaluate(ctx, P, I, at_candidate ? I.cand : I.w, flags);
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_lq_begin(DevProblem P, Batch B, Options o, int warmstart)
+{
+    KERNEL_PROLOGUE
+    solve_begin_lq(ctx, P, I, o, warmstart);
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_lq_step(DevProblem P, Batch B, Options o)
+{
+    KERNEL_PROLOGUE
+    solve_step_lq(ctx, P, I, o);
+}
+
+// LinearSolver seam: factor the generic matrix / solve in place.  These two are the "KKT LDL^T solve" whose HBM
+// roofline bench.py reports (B_unit).
+__global__ void __launch_bounds__(CB_THREADS) k_ldl_factor(DevProblem P, Batch B, int assemble_generic)
+{
+    __shared__ double red[34];
+    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red};
+    const int b = blockIdx.x;
+    if (b >= B.count) return;
+    double *pan = B.panels + b * P.panel_total;
+    double *D = B.D + b * (long long)P.N, *Dinv = B.Dinv + b * (long long)P.N;
+    int *istat = B.istat + b * (long long)I_COUNT;
+    if (assemble_generic) matrix_assemble(ctx, P, pan, B.Aval + b * (long long)P.nnzA);
+    ldl_factor(ctx, P, pan, D, Dinv, istat);
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_ldl_solve(DevProblem P, Batch B)
+{
+    __shared__ double red[34];
+    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red};
+    const int b = blockIdx.x;
+    if (b >= B.count) return;
+    double *rhs = B.rhs + b * (long long)P.N;
+    ldl_solve(ctx, P, B.panels + b * P.panel_total, B.Dinv + b * (long long)P.N, rhs, rhs, B.xp + b * (long long)P.N,
+              B.istat + b * (long long)I_COUNT);
+}
+
+// KKT path: assemble + factor with the current regularisation (no inertia loop) -- used by the roofline bench
+__global__ void __launch_bounds__(CB_THREADS) k_kkt_factor_solve(DevProblem P, Batch B, int nsolves)
+{
+    KERNEL_PROLOGUE
+    kkt_assemble(ctx, P, I);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.istat);
+    for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
+}
+
+__global__ void k_count_states(Batch B, long long *counts)
+{
+    __shared__ int c[4];
+    if (threadIdx.x < 4) c[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B.count; b += blockDim.x) atomicAdd(&c[B.istat[b * (long long)I_COUNT + I_CONVERGED] & 3], 1);
+    __syncthreads();
+    if (threadIdx.x < 4) counts[threadIdx.x] = c[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return -1; }
+#define CUDA_OK(x)                                                                                      \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct ArrayDesc { double *ptr; long long len; };
+
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+};
+static NcclApi g_nccl;
+
+struct cb200_handle {
+    int device = 0, batch = 0;
+    bool generic = false;
+    cudaStream_t stream = nullptr;
+    HostProblem hp;        // KKT handles
+    Symbolic gsym;         // LinearSolver-seam handles
+    const Symbolic &sym() const { return generic ? gsym : hp.sym; }
+    DevProblem P{};
+    Batch B{};
+    Options opt{};
+    std::vector<void *> allocs;
+    ArrayDesc arr[CB200_NUM_ARRAYS]{};
+    long long *d_counts = nullptr, *h_counts = nullptr;
+    void *comm = nullptr;
+    int nranks = 1;
+    int nnzW = 0, nnzG = 0, nnzC = 0;
+};
+
+extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" void cb200_options_default(cb200_options *o)
+{   // options.jl:6-59
+    memset(o, 0, sizeof(*o));
+    o->max_outer_iterations = 10; o->max_residual_iterations = 100; o->max_residual_line_search = 25;
+    o->max_cone_line_search = 25; o->iterative_refinement = 1; o->max_iterative_refinement = 10;
+    o->min_iterative_refinement = 1; o->scaling_line_search = 0.5; o->iterative_refinement_tolerance = 1.0e-10;
+    o->central_path_initial = 1.0; o->central_path_update_tolerance = 10.0; o->central_path_scaling = 0.2;
+    o->central_path_exponent = 1.5; o->penalty_initial = 1.0; o->penalty_scaling = 10.0; o->dual_initial = 0.0;
+    o->residual_tolerance = 1.0e-4; o->optimality_tolerance = 1.0e-4; o->slack_tolerance = 1.0e-4;
+    o->equality_tolerance = 1.0e-4; o->complementarity_tolerance = 1.0e-4; o->min_regularization = 1.0e-20;
+    o->primal_regularization_initial = 1.0e-7; o->dual_regularization_initial = 1.0e-7;
+    o->max_regularization = 1.0e40; o->dual_regularization = 1.0e-8; o->dual_regularization_exponent = 0.25;
+    o->scaling_regularization_initial = 100.0; o->scaling_regularization = 8.0;
+    o->scaling_regularization_last = 1.0 / 3.0; o->max_penalty = 1.0e8; o->violation_tolerance = 1.0e-5;
+    o->violation_exponent = 1.1; o->merit_tolerance = 1.0e-5; o->merit_exponent = 2.3; o->armijo_tolerance = 1.0e-4;
+    o->machine_tolerance = 1.0e-16; o->max_filter = 1000; o->gmres_restart = 30; o->gmres_max_cycles = 10;
+}
+
+template <class T> static const T *upload(cb200_handle *h, const std::vector<T> &v, bool &ok)
+{
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { ok = false; return nullptr; }
+    h->allocs.push_back(d);
+    if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    return (const T *)d;
+}
+
+static double *dalloc(cb200_handle *h, long long per_instance, bool &ok, bool zero = true)
+{
+    void *d = nullptr;
+    size_t bytes = (size_t)std::max<long long>(per_instance * h->batch, 1) * sizeof(double);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { ok = false; return nullptr; }
+    h->allocs.push_back(d);
+    if (zero && cudaMemset(d, 0, bytes) != cudaSuccess) ok = false;
+    return (double *)d;
+}
+
+static int common_init(cb200_handle *h, int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: libcalipso_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("invalid device index");
+    h->device = device;
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc(&h->d_counts, 4 * sizeof(long long)));
+    CUDA_OK(cudaMallocHost(&h->h_counts, 4 * sizeof(long long)));
+    return 0;
+}
+
+static const int BIG_TASK_THRESHOLD = 3000;   // multiply-adds above which a supernode gets the whole CTA
+
+extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, int nsoc, const int *soc_dims,
+                                      const int *Wp, const int *Wi, const int *Gp, const int *Gi, const int *Cp,
+                                      const int *Ci, const int *perm, const cb200_options *options, int device)
+{
+    if (batch <= 0 || n <= 0 || m < 0 || p < 0) { fail("invalid dimensions"); return nullptr; }
+    cb200_handle *h = new cb200_handle();
+    h->batch = batch;
+    if (common_init(h, device)) { delete h; return nullptr; }
+    cb200_options dflt;
+    cb200_options_default(&dflt);
+    memcpy(&h->opt, options ? options : &dflt, sizeof(Options));
+    DevProblem &P = h->P;
+    {
+        std::string msg = h->hp.build(n, m, p, q_nn, nsoc, soc_dims, Wp, Wi, Gp, Gi, Cp, Ci, perm, BIG_TASK_THRESHOLD);
+        if (!msg.empty()) { fail(msg); cb200_destroy(h); return nullptr; }
+    }
+    const int nnzW = h->hp.nnzW, nnzG = h->hp.nnzG, nnzC = h->hp.nnzC, N = h->hp.N;
+    h->nnzW = nnzW; h->nnzG = nnzG; h->nnzC = nnzC;
+    bool ok = true;
+    fill_problem(P, h->hp, [&](const auto &v) { return upload(h, v, ok); });
+    // per-instance storage
+    Batch &B = h->B;
+    const long long T = P.total;
+    B.count = batch; B.F = h->opt.max_filter;
+    const int mr = h->opt.gmres_restart;
+    B.ksize = mr > 0 ? (long long)(mr + 1) * T + (long long)(mr + 1) * mr + 4LL * mr + 8 : 0;
+    B.w = dalloc(h, T, ok); B.cand = dalloc(h, T, ok); B.step = dalloc(h, T, ok); B.res = dalloc(h, T, ok);
+    B.err = dalloc(h, T, ok); B.corr = dalloc(h, T, ok); B.tmp = dalloc(h, T, ok);
+    B.grad = dalloc(h, n, ok); B.gyx = dalloc(h, n, ok); B.hzx = dalloc(h, n, ok);
+    B.g = dalloc(h, m, ok); B.h = dalloc(h, p, ok);
+    B.Wv = dalloc(h, nnzW, ok); B.Gv = dalloc(h, nnzG, ok); B.Cv = dalloc(h, nnzC, ok);
+    B.prod = dalloc(h, p, ok); B.bgrad = dalloc(h, p, ok); B.lambda = dalloc(h, m, ok);
+    B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
+    B.xs = dalloc(h, N, ok); B.rs = dalloc(h, N, ok); B.xp = dalloc(h, N, ok); B.mgrad = dalloc(h, N, ok);
+    B.q = dalloc(h, n, ok); B.g0 = dalloc(h, m, ok); B.h0 = dalloc(h, p, ok);
+    B.filter = dalloc(h, 4LL * B.F, ok);
+    B.krylov = B.ksize ? dalloc(h, B.ksize, ok, false) : nullptr;
+    B.scal = dalloc(h, S_COUNT, ok);
+    B.Aval = nullptr; B.rhs = nullptr;
+    {
+        void *d = nullptr;
+        size_t bytes = (size_t)batch * I_COUNT * sizeof(int);
+        if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemset(d, 0, bytes) != cudaSuccess) ok = false;
+        h->allocs.push_back(d);
+        B.istat = (int *)d;
+    }
+    if (!ok) { fail(std::string("device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError())); cb200_destroy(h); return nullptr; }
+    ArrayDesc *a = h->arr;
+    a[CB200_POINT] = {B.w, T}; a[CB200_CANDIDATE] = {B.cand, T}; a[CB200_STEP] = {B.step, T};
+    a[CB200_RESIDUAL] = {B.res, T}; a[CB200_GRADIENT] = {B.grad, n}; a[CB200_EQ_DUAL_GRAD] = {B.gyx, n};
+    a[CB200_CONE_DUAL_GRAD] = {B.hzx, n}; a[CB200_EQUALITY] = {B.g, m}; a[CB200_CONE] = {B.h, p};
+    a[CB200_W_VALUES] = {B.Wv, nnzW}; a[CB200_G_VALUES] = {B.Gv, nnzG}; a[CB200_C_VALUES] = {B.Cv, nnzC};
+    a[CB200_CONE_PRODUCT] = {B.prod, p}; a[CB200_BARRIER_GRADIENT] = {B.bgrad, p}; a[CB200_DUAL] = {B.lambda, m};
+    a[CB200_LQ_Q] = {B.q, n}; a[CB200_LQ_G0] = {B.g0, m}; a[CB200_LQ_H0] = {B.h0, p};
+    a[CB200_SCALARS] = {B.scal, S_COUNT}; a[CB200_MERIT_GRADIENT] = {B.mgrad, N};
+    a[CB200_RESIDUAL_SYMMETRIC] = {B.rs, N}; a[CB200_STEP_SYMMETRIC] = {B.xs, N}; a[CB200_PIVOTS] = {B.D, N};
+    a[CB200_MATRIX_VALUES] = {nullptr, 0}; a[CB200_RHS] = {nullptr, 0}; a[CB200_PANELS] = {B.panels, P.panel_total};
+    // solver.jl:81-86,125-127 initial scalars
+    std::vector<double> sc((size_t)batch * S_COUNT, 0.0);
+    for (int b = 0; b < batch; b++) { sc[(size_t)b * S_COUNT + S_KAPPA] = 0.1; sc[(size_t)b * S_COUNT + S_TAU] = 0.99; sc[(size_t)b * S_COUNT + S_RHO] = 10.0; }
+    cudaMemcpy(B.scal, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice);
+    return h;
+}
+
+extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const int *Ai, const int *perm, int device)
+{
+    if (batch <= 0 || N <= 0) { fail("invalid dimensions"); return nullptr; }
+    cb200_handle *h = new cb200_handle();
+    h->batch = batch;
+    h->generic = true;
+    if (common_init(h, device)) { delete h; return nullptr; }
+    cb200_options dflt;
+    cb200_options_default(&dflt);
+    memcpy(&h->opt, &dflt, sizeof(Options));
+    const char *msg = h->gsym.analyze(N, Ap, Ai, perm, BIG_TASK_THRESHOLD);
+    if (msg[0]) { fail(msg); cb200_destroy(h); return nullptr; }
+    DevProblem &P = h->P;
+    bool ok = true;
+    fill_symbolic(P, h->gsym, [&](const auto &v) { return upload(h, v, ok); });
+    P.nnzA = Ap[N];
+    P.dA = upload(h, h->gsym.dest, ok);
+    Batch &B = h->B;
+    B.count = batch;
+    B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
+    B.xp = dalloc(h, N, ok); B.Aval = dalloc(h, P.nnzA, ok); B.rhs = dalloc(h, N, ok);
+    {
+        void *d = nullptr;
+        size_t bytes = (size_t)batch * I_COUNT * sizeof(int);
+        if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemset(d, 0, bytes) != cudaSuccess) ok = false;
+        h->allocs.push_back(d);
+        B.istat = (int *)d;
+    }
+    if (!ok) { fail("device allocation/upload failed"); cb200_destroy(h); return nullptr; }
+    h->arr[CB200_PIVOTS] = {B.D, N};
+    h->arr[CB200_MATRIX_VALUES] = {B.Aval, P.nnzA};
+    h->arr[CB200_RHS] = {B.rhs, N};
+    h->arr[CB200_PANELS] = {B.panels, P.panel_total};
+    return h;
+}
+
+extern "C" void cb200_destroy(cb200_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->d_counts) cudaFree(h->d_counts);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int cb200_info(const cb200_handle *h, long long *out)
+{
+    const Symbolic &S = h->sym();
+    out[0] = S.N; out[1] = h->P.total; out[2] = S.nnzA; out[3] = S.nnzL; out[4] = S.ns; out[5] = S.nlevels;
+    out[6] = (long long)S.phases.size(); out[7] = S.max_w; out[8] = S.max_nrow; out[9] = S.panel_total;
+    out[10] = S.flops; out[11] = h->batch; out[12] = h->P.n; out[13] = h->P.m; out[14] = h->P.p;
+    out[15] = (long long)h->nnzW + h->nnzG + h->nnzC;
+    return 0;
+}
+
+extern "C" int cb200_get_symbolic(const cb200_handle *h, int *perm, int *etree, int *Lnz)
+{
+    const Symbolic &S = h->sym();
+    if (perm) memcpy(perm, S.perm.data(), sizeof(int) * S.N);
+    if (etree) memcpy(etree, S.etree.data(), sizeof(int) * S.N);
+    if (Lnz) memcpy(Lnz, S.Lnz.data(), sizeof(int) * S.N);
+    return 0;
+}
+
+extern "C" int cb200_get_factor(cb200_handle *h, int instance, int *Lp, int *Li, double *Lx, double *D)
+{
+    if (instance < 0 || instance >= h->batch) return fail("instance out of range");
+    const Symbolic &S = h->sym();
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    std::vector<double> pan((size_t)S.panel_total);
+    CUDA_OK(cudaMemcpy(pan.data(), h->B.panels + (long long)instance * S.panel_total, sizeof(double) * pan.size(), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(D, h->B.D + (long long)instance * S.N, sizeof(double) * S.N, cudaMemcpyDeviceToHost));
+    Lp[0] = 0;
+    for (int s = 0; s < S.ns; s++) {
+        int c0 = S.sn_start[s], c1 = S.sn_start[s + 1], w = c1 - c0;
+        int nR = S.rows_ptr[s + 1] - S.rows_ptr[s], nrow = w + nR;
+        const double *Ps = pan.data() + S.panel_off[s];
+        for (int c = c0; c < c1; c++) {
+            int k = Lp[c];
+            for (int r = c + 1; r < c1; r++) { Li[k] = r; Lx[k] = Ps[(r - c0) + (long long)(c - c0) * nrow]; k++; }
+            for (int i = 0; i < nR; i++) { Li[k] = S.rows[S.rows_ptr[s] + i]; Lx[k] = Ps[(w + i) + (long long)(c - c0) * nrow]; k++; }
+            Lp[c + 1] = k;
+        }
+    }
+    return 0;
+}
+
+static int check_array(cb200_handle *h, int which, int first, int count)
+{
+    if (which < 0 || which >= CB200_NUM_ARRAYS || !h->arr[which].ptr) return fail("array not available on this handle");
+    if (first < 0 || count < 0 || first + count > h->batch) return fail("instance range out of bounds");
+    return 0;
+}
+
+extern "C" int cb200_set_array(cb200_handle *h, int which, const double *host, int first, int count)
+{
+    if (check_array(h, which, first, count)) return -1;
+    CUDA_OK(cudaSetDevice(h->device));
+    const ArrayDesc &a = h->arr[which];
+    CUDA_OK(cudaMemcpyAsync(a.ptr + (long long)first * a.len, host, sizeof(double) * a.len * count, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+extern "C" int cb200_get_array(cb200_handle *h, int which, double *host, int first, int count)
+{
+    if (check_array(h, which, first, count)) return -1;
+    CUDA_OK(cudaSetDevice(h->device));
+    const ArrayDesc &a = h->arr[which];
+    CUDA_OK(cudaMemcpyAsync(host, a.ptr + (long long)first * a.len, sizeof(double) * a.len * count, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int cb200_get_stats(cb200_handle *h, int *host, int first, int count)
+{
+    if (first < 0 || count < 0 || first + count > h->batch) return fail("instance range out of bounds");
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaMemcpyAsync(host, h->B.istat + (long long)first * I_COUNT, sizeof(int) * I_COUNT * count, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int cb200_array_length(const cb200_handle *h, int which)
+{
+    if (which < 0 || which >= CB200_NUM_ARRAYS || !h->arr[which].ptr) return -1;
+    return (int)h->arr[which].len;
+}
+extern "C" void *cb200_device_ptr(cb200_handle *h, int which)
+{
+    if (which < 0 || which >= CB200_NUM_ARRAYS) return nullptr;
+    return h->arr[which].ptr;
+}
+extern "C" void *cb200_stream(cb200_handle *h) { return (void *)h->stream; }
+extern "C" int cb200_synchronize(cb200_handle *h)
+{
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
+{
+    if (o->max_filter != h->opt.max_filter || o->gmres_restart != h->opt.gmres_restart)
+        return fail("max_filter / gmres_restart are fixed at creation");
+    memcpy(&h->opt, o, sizeof(Options));
+    return 0;
+}
+
+#define LAUNCH(kernel, ...)                                                   \
+    do {                                                                      \
+        CUDA_OK(cudaSetDevice(h->device));                                    \
+        kernel<<<h->batch, CB_THREADS, 0, h->stream>>>(__VA_ARGS__);          \
+        CUDA_OK(cudaGetLastError());                                          \
+    } while (0)
+#define NEED_KKT() if (h->generic) return fail("not available on a LinearSolver-seam handle")
+
+extern "C" int cb200_cone(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); LAUNCH(k_cone, h->P, h->B, flags, at_candidate); return 0; }
+extern "C" int cb200_residual(cb200_handle *h) { NEED_KKT(); LAUNCH(k_residual, h->P, h->B); return 0; }
+extern "C" int cb200_search_direction(cb200_handle *h) { NEED_KKT(); LAUNCH(k_search_direction, h->P, h->B, h->opt); return 0; }
+extern "C" int cb200_cone_search(cb200_handle *h) { NEED_KKT(); LAUNCH(k_cone_search, h->P, h->B, h->opt); return 0; }
+extern "C" int cb200_apply_step(cb200_handle *h) { NEED_KKT(); LAUNCH(k_apply_step, h->P, h->B); return 0; }
+extern "C" int cb200_lq_evaluate(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); LAUNCH(k_lq_evaluate, h->P, h->B, flags, at_candidate); return 0; }
+extern "C" int cb200_lq_begin(cb200_handle *h, int warmstart) { NEED_KKT(); LAUNCH(k_lq_begin, h->P, h->B, h->opt, warmstart); return 0; }
+extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
+{
+    NEED_KKT();
+    for (int k = 0; k < iterations; k++) LAUNCH(k_lq_step, h->P, h->B, h->opt);
+    return 0;
+}
+extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); LAUNCH(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
+
+extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host)
+{
+    NEED_KKT();
+    CUDA_OK(cudaSetDevice(h->device));
+    size_t bytes = sizeof(double) * h->P.total * (size_t)h->batch;
+    CUDA_OK(cudaMemcpyAsync(h->B.err, v_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_jtimes, h->P, h->B);
+    CUDA_OK(cudaMemcpyAsync(out_host, h->B.tmp, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int cb200_allreduce_counts(cb200_handle *h, long long *counts)
+{
+    CUDA_OK(cudaSetDevice(h->device));
+    k_count_states<<<1, 256, 0, h->stream>>>(h->B, h->d_counts);
+    CUDA_OK(cudaGetLastError());
+    if (h->comm) {
+        int rc = g_nccl.AllReduce(h->d_counts, h->d_counts, 4, /*ncclInt64*/ 4, /*ncclSum*/ 0, h->comm, h->stream);
+        if (rc != 0) return fail("ncclAllReduce failed with code " + std::to_string(rc));
+    }
+    CUDA_OK(cudaMemcpyAsync(h->h_counts, h->d_counts, 4 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; k++) counts[k] = h->h_counts[k];
+    return 0;
+}
+
+extern "C" int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, long long *counts, int *steps_done)
+{
+    NEED_KKT();
+    if (check_every <= 0) check_every = 1;
+    int done = 0;
+    long long c[4] = {h->batch, 0, 0, 0};
+    while (done < max_steps) {
+        int chunk = std::min(check_every, max_steps - done);
+        if (cb200_lq_step(h, chunk)) return -1;
+        done += chunk;
+        if (cb200_allreduce_counts(h, c)) return -1;
+        if (c[0] == 0) break;
+    }
+    if (counts) for (int k = 0; k < 4; k++) counts[k] = c[k];
+    if (steps_done) *steps_done = done;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- LinearSolver seam
+extern "C" int cb200_ldl_factorize(cb200_handle *h)
+{
+    if (!h->generic) return fail("cb200_ldl_factorize needs a handle from cb200_ldl_create");
+    LAUNCH(k_ldl_factor, h->P, h->B, 1);
+    return 0;
+}
+extern "C" int cb200_ldl_solve(cb200_handle *h)
+{
+    if (!h->generic) return fail("cb200_ldl_solve needs a handle from cb200_ldl_create");
+    LAUNCH(k_ldl_solve, h->P, h->B);
+    return 0;
+}
+extern "C" int cb200_ldl_inertia(cb200_handle *h, int *out)
+{
+    std::vector<int> st((size_t)h->batch * I_COUNT);
+    if (cb200_get_stats(h, st.data(), 0, h->batch)) return -1;
+    for (int b = 0; b < h->batch; b++)
+        for (int k = 0; k < 3; k++) out[3 * b + k] = st[(size_t)b * I_COUNT + k];
+    return 0;
+}
+extern "C" int cb200_ldl_linear_solve(cb200_handle *h, const double *Ax, const double *bvec, double *x, int factorize)
+{
+    if (!h->generic) return fail("cb200_ldl_linear_solve needs a handle from cb200_ldl_create");
+    if (factorize) {
+        if (cb200_set_array(h, CB200_MATRIX_VALUES, Ax, 0, h->batch)) return -1;
+        if (cb200_ldl_factorize(h)) return -1;
+    }
+    if (cb200_set_array(h, CB200_RHS, bvec, 0, h->batch)) return -1;
+    if (cb200_ldl_solve(h)) return -1;
+    return cb200_get_array(h, CB200_RHS, x, 0, h->batch);
+}
+
+// ---------------------------------------------------------------------------------------------------- NCCL (dlopen'd)
+static int load_nccl()
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(std::string("cannot load NCCL: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return fail("NCCL symbols missing");
+    return 0;
+}
+
+extern "C" int cb200_nccl_unique_id(char *out128)
+{
+    if (load_nccl()) return -1;
+    NcclId id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail("ncclGetUniqueId failed with code " + std::to_string(rc));
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+extern "C" int cb200_comm_init(cb200_handle *h, int rank, int nranks, const char *unique_id128)
+{
+    if (load_nccl()) return -1;
+    CUDA_OK(cudaSetDevice(h->device));
+    NcclId id;
+    memcpy(id.internal, unique_id128, 128);
+    int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc != 0) { h->comm = nullptr; return fail("ncclCommInitRank failed with code " + std::to_string(rc)); }
+    h->nranks = nranks;
+    return 0;
+}

@@ -1,0 +1,926 @@
+// device_core.h -- CTA-cooperative building blocks of the B200 Newton/KKT path.
+//
+// One CTA owns one problem instance.  Every routine below is written as "parallel-for over an index range, then
+// barrier": under nvcc the index ranges are strided over the threads of the cooperating scope (whole CTA or one
+// warp) and barriers are __syncthreads()/__syncwarp(); when this header is compiled by a host compiler with
+// CB200_HOST_EMULATION (tests only -- never linked into the product library) the same source runs the index ranges
+// sequentially so that the numerical logic can be checked on a machine without a GPU.
+//
+// Reference map (function -> reference file:line it replaces):
+//   cone_eval            cones/cone.jl:71-106, nonnegative.jl:11-15, second_order.jl:13-17
+//   residual_eval        residual.jl:1-51 + norms solve.jl:130-135, optimality_error.jl:1-27
+//   kkt_assemble         residual_jacobian_variables.jl:1-167 (full J never materialised; K written straight into
+//                        the supernodal panels = triu! + update_values!, linear_solver.jl:23-24, qdldl.jl:199-213)
+//   ldl_factor           refactor!/QDLDL_factor!, qdldl.jl:269-278,400-589 + compute_inertia!, linear_solver.jl:33-44
+//   ldl_solve            solve!/QDLDL_solve!, qdldl.jl:330-351,592-640
+//   reduced_rhs          residual_symmetric!, residual.jl:53-101
+//   recover_step         search_direction_symmetric! recovery, search_direction.jl:45-101
+//   jacobian_times       mul!(.., jacobian_variables, ..), iterative_refinement.jl:9,39
+//   search_direction     search_direction.jl:1-23 + inertia.jl:30-79 + iterative_refinement.jl:1-53
+//   cone_search          solve.jl:190-221, cones/cone.jl:62-68
+#pragma once
+
+#include <math.h>
+
+#include "symbolic.h"
+
+#if defined(__CUDACC__) && !defined(CB200_HOST_EMULATION)
+#define CB_DEV __device__ __forceinline__
+#define CB_DEVN __device__ __noinline__
+#define CB_ON_DEVICE 1
+#else
+#define CB_DEV inline
+#define CB_DEVN inline
+#define CB_ON_DEVICE 0
+#endif
+
+namespace cb200 {
+
+// ------------------------------------------------------------------------------------------------ shared data
+struct Csr {          // row-wise view of a CSC matrix: entry k of row i is value[src[k]] at column col[k]
+    const int *ptr, *col, *src;
+};
+
+struct DevProblem {   // everything shared by the instances of a batch (device pointers)
+    int n, m, p, N, total;
+    int q_nn, nsoc, tri_total;
+    int nnzW, nnzG, nnzC;
+    const int *soc_off, *soc_dims, *soc_tri;  // soc_tri[k]: offset of cone k's upper-triangle entries in dZsoc
+    // patterns
+    const int *Wp, *Wi, *Wdiag;               // upper triangle CSC, Wdiag[j] = position of (j,j)
+    Csr Wfull;                                 // symmetric W by rows (both triangles), src -> position in W values
+    const int *Gp, *Gi, *Cp, *Ci;              // CSC
+    Csr Grow, Crow;
+    // symbolic factorisation
+    int ns, nphases, max_w, max_nrow;
+    long long panel_total;
+    const int *perm;
+    const int *sn_start, *rows_ptr, *rows;
+    const long long *panel_off;
+    const int *upd_ptr;
+    const UpdateEntry *upd;
+    const int *rel;
+    const int *order;
+    const Phase *phases;
+    const int *fwd_ptr, *fwd_d, *fwd_row;      // per permuted column: (descendant supernode, local row) pairs
+    // assembly destinations (offsets into the panel storage)
+    const long long *dW, *dG, *dC, *dY, *dZnn, *dZsoc;
+    const long long *dA;                       // generic-matrix mode (LinearSolver seam): one per input entry
+    int nnzA;
+};
+
+struct Options {      // src/solver/options.jl:6-59, hot-path subset (same defaults, see api.cu)
+    int max_outer_iterations, max_residual_iterations, max_residual_line_search, max_cone_line_search;
+    int iterative_refinement, max_iterative_refinement, min_iterative_refinement;
+    double scaling_line_search, iterative_refinement_tolerance;
+    double central_path_initial, central_path_update_tolerance, central_path_scaling, central_path_exponent;
+    double penalty_initial, penalty_scaling, dual_initial;
+    double residual_tolerance, optimality_tolerance, slack_tolerance, equality_tolerance, complementarity_tolerance;
+    double min_regularization, primal_regularization_initial, dual_regularization_initial, max_regularization;
+    double dual_regularization, dual_regularization_exponent;
+    double scaling_regularization_initial, scaling_regularization, scaling_regularization_last;
+    double max_penalty;
+    double violation_tolerance, violation_exponent, merit_tolerance, merit_exponent, armijo_tolerance,
+        machine_tolerance;
+    int max_filter;
+    int gmres_restart, gmres_max_cycles;   // fallback when refinement fails (replaces the reference's UMFPACK J\R)
+};
+
+// per-instance scalar slots
+enum {
+    S_KAPPA = 0, S_TAU, S_RHO, S_EPSP, S_EPSD, S_EPSP_LAST, S_OBJECTIVE, S_BARRIER,
+    S_RESIDUAL_VIOLATION, S_OPTIMALITY_VIOLATION, S_SLACK_VIOLATION, S_THETA, S_MERIT,
+    S_STEP_SIZE, S_STEP_SIZE_T, S_EQUALITY_VIOLATION, S_CONE_PRODUCT_VIOLATION,
+    S_REFINE_NORM, S_REFINE_NORM_INITIAL, S_MERIT_CANDIDATE, S_THETA_CANDIDATE, S_COUNT = 24
+};
+enum {
+    I_INERTIA_POS = 0, I_INERTIA_NEG, I_INERTIA_ZERO, I_TRIALS, I_REFINE, I_REFINE_OK, I_KS, I_KT, I_STATUS,
+    I_USED_FALLBACK, I_FALLBACKS, I_TOTAL_ITERATIONS, I_OUTER, I_LINE_SEARCH, I_CONVERGED, I_GMRES_ITERS,
+    I_FILTER_INDEX, I_INNER, I_FACTORIZATIONS, I_SOLVES, I_COUNT = 24
+};
+// status codes (also the C ABI's, include/calipso_b200.h)
+enum { ST_OK = 0, ST_INERTIA_FAILURE = 1, ST_REFINEMENT_FAILURE = 2, ST_CONE_SEARCH_FAILURE = 3, ST_ZERO_PIVOT = 4 };
+
+struct Inst {         // device pointers of ONE instance
+    double *w, *cand, *step, *res, *err, *corr, *tmp;  // [total]
+    double *grad, *gyx, *hzx;                          // [n]
+    double *g, *h;                                     // [m], [p]
+    double *Wv, *Gv, *Cv;                              // values at the patterns
+    double *prod, *bgrad;                              // [p]
+    double *lambda;                                    // [m]
+    double *panels, *D, *Dinv;                         // factor
+    double *xs, *rs, *xp;                              // [N] reduced solution / rhs / permuted scratch
+    double *mgrad;                                     // [N]
+    double *q, *g0, *h0;                               // LQ data (may be null)
+    double *filter;                                    // [2*max_filter]
+    double *krylov;                                    // [(restart+1) * total] GMRES basis (may be null)
+    double *scal;                                      // [S_COUNT]
+    int *istat;                                        // [I_COUNT]
+};
+
+// ------------------------------------------------------------------------------------------------ cooperation scope
+struct Ctx {
+    int tid, nthr;     // thread index / count inside the cooperating scope
+    int warp_scope;    // 1: the scope is a single warp
+    double *red;       // CTA scratch for reductions (>= 34 doubles), unused in warp scope
+    CB_DEV void sync() const
+    {
+#if CB_ON_DEVICE
+        if (warp_scope) __syncwarp(); else __syncthreads();
+#endif
+    }
+};
+
+#if CB_ON_DEVICE
+#define PAR_FOR(i, count) for (int i = ctx.tid; i < (count); i += ctx.nthr)
+#else
+#define PAR_FOR(i, count) for (int i = 0; i < (count); i++)
+#endif
+
+// Reductions over f(i), i in [0,n): every thread of the scope returns the same value.  Fixed association order
+// (thread-strided partials, shuffle tree, warp partials in warp order) => run-to-run deterministic.
+template <class F> CB_DEV double scope_sum(const Ctx &ctx, int n, F f)
+{
+    double a = 0.0;
+    PAR_FOR(i, n) a += f(i);
+#if CB_ON_DEVICE
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (ctx.warp_scope) return a;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) ctx.red[wid] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < nw; k++) t += ctx.red[k];
+        ctx.red[33] = t;
+    }
+    __syncthreads();
+    a = ctx.red[33];
+#endif
+    return a;
+}
+
+template <class F> CB_DEV double scope_max(const Ctx &ctx, int n, F f)
+{
+    double a = 0.0;  // all uses are maxima of absolute values
+    PAR_FOR(i, n) { double v = f(i); a = v > a ? v : a; }
+#if CB_ON_DEVICE
+    for (int o = 16; o > 0; o >>= 1) { double b = __shfl_xor_sync(0xffffffffu, a, o); a = b > a ? b : a; }
+    if (ctx.warp_scope) return a;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) ctx.red[wid] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < nw; k++) t = ctx.red[k] > t ? ctx.red[k] : t;
+        ctx.red[33] = t;
+    }
+    __syncthreads();
+    a = ctx.red[33];
+#endif
+    return a;
+}
+
+// integer "any" over the scope (used for violation tests)
+template <class F> CB_DEV int scope_any(const Ctx &ctx, int n, F f)
+{
+    return scope_max(ctx, n, [&](int i) { return f(i) ? 1.0 : 0.0; }) > 0.5;
+}
+
+// ------------------------------------------------------------------------------------------------ second-order cone algebra
+// arrow(u)^-1 x with the reference's closed form and operation order (second_order.jl:50-61); u, x given as
+// element functors so that no temporary vectors are needed; out(i, value) receives the result.
+template <class U, class X, class O> CB_DEV void soc_arrow_inverse(int d, U u, X x, O out)
+{
+    double u1 = u(0);
+    double uu = 0.0;
+    for (int i = 1; i < d; i++) uu += u(i) * u(i);
+    double alpha = -1.0 / (u1 * u1) * uu;
+    double beta = 1.0 / (1.0 + alpha);
+    double acc = 0.0;
+    for (int i = 1; i < d; i++) acc += (u(i) / u1) * x(i);
+    double x0_1 = x(0) - acc;
+    double acc2 = 0.0;
+    for (int i = 1; i < d; i++) {
+        double x1_i = x(i) - beta * ((u(i) / u1) * x0_1);
+        acc2 += (u(i) / u1) * x1_i;
+        out(i, 1.0 / u1 * x1_i);
+    }
+    out(0, 1.0 / u1 * (x(0) - acc2));
+}
+
+// [arrow(a) v]_i given dot = a . v
+CB_DEV double arrow_apply(const double *a, const double *v, int i, double dot)
+{
+    return i == 0 ? dot : a[0] * v[i] + v[0] * a[i];
+}
+
+// ------------------------------------------------------------------------------------------------ cone!
+CB_DEVN void cone_eval(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *w, int barrier,
+                       int barrier_gradient, int product)
+{
+    const double *s = w + P.n + P.m, *t = w + P.n + 2 * P.m + 2 * P.p;
+    if (barrier) {
+        double nn = scope_sum(ctx, P.q_nn, [&](int i) { return log(s[i]); });
+        double so = scope_sum(ctx, P.nsoc, [&](int k) {
+            const double *x = s + P.soc_off[k];
+            int d = P.soc_dims[k];
+            if (d <= 0) return 0.0;
+            double tt = 0.0;
+            for (int i = 1; i < d; i++) tt += x[i] * x[i];
+            return 0.5 * log(x[0] * x[0] - tt);
+        });
+        if (ctx.tid == 0) I.scal[S_BARRIER] = nn + so;
+    }
+    if (barrier_gradient) {
+        PAR_FOR(i, P.q_nn) I.bgrad[i] = 1.0 / s[i];
+        PAR_FOR(k, P.nsoc) {
+            const double *x = s + P.soc_off[k];
+            double *g = I.bgrad + P.soc_off[k];
+            int d = P.soc_dims[k];
+            if (d > 0) {
+                double tt = 0.0;
+                for (int i = 1; i < d; i++) tt += x[i] * x[i];
+                double c = 1.0 / (x[0] * x[0] - tt);
+                g[0] = c * x[0];
+                for (int i = 1; i < d; i++) g[i] = c * (-x[i]);
+            }
+        }
+    }
+    if (product) {
+        PAR_FOR(i, P.q_nn) I.prod[i] = s[i] * t[i];
+        PAR_FOR(k, P.nsoc) {
+            const double *a = s + P.soc_off[k], *b = t + P.soc_off[k];
+            double *o = I.prod + P.soc_off[k];
+            int d = P.soc_dims[k];
+            if (d > 0) {
+                double dot = 0.0;
+                for (int i = 0; i < d; i++) dot += a[i] * b[i];
+                o[0] = dot;
+                for (int i = 1; i < d; i++) o[i] = a[0] * b[i] + b[0] * a[i];
+            }
+        }
+    }
+    ctx.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ residual! + norms
+CB_DEVN void residual_eval(const Ctx &ctx, const DevProblem &P, const Inst &I)
+{
+    const int n = P.n, m = P.m, p = P.p;
+    const double *w = I.w;
+    const double *r = w + n, *s = w + n + m, *y = w + n + m + p, *z = w + n + 2 * m + p, *t = w + n + 2 * m + 2 * p;
+    double *res = I.res;
+    const double kappa = I.scal[S_KAPPA], rho = I.scal[S_RHO];
+    PAR_FOR(i, n) res[i] = I.grad[i] + I.gyx[i] + I.hzx[i];
+    PAR_FOR(i, m) {
+        res[n + i] = I.lambda[i] + rho * r[i] - y[i];
+        res[n + m + p + i] = I.g[i] - r[i];
+    }
+    PAR_FOR(i, p) {
+        res[n + m + i] = -z[i] - t[i];
+        res[n + 2 * m + p + i] = I.h[i] - s[i];
+    }
+    PAR_FOR(i, P.q_nn) res[n + 2 * m + 2 * p + i] = I.prod[i] - kappa;
+    PAR_FOR(k, P.nsoc) {
+        int c0 = P.soc_off[k], d = P.soc_dims[k];
+        for (int i = 0; i < d; i++) res[n + 2 * m + 2 * p + c0 + i] = I.prod[c0 + i] - (i == 0 ? kappa : 0.0);
+    }
+    ctx.sync();
+    // violations (solve.jl:130-135, optimality_error.jl:1-27)
+    double r1 = scope_sum(ctx, P.total, [&](int i) { return fabs(res[i]); });
+    double lag = scope_max(ctx, n + m + p, [&](int i) { return fabs(res[i]); });
+    double eq = scope_max(ctx, m, [&](int i) { return fabs(res[n + m + p + i]); });
+    double cn = scope_max(ctx, p, [&](int i) { return fabs(res[n + 2 * m + p + i]); });
+    double cp = scope_max(ctx, p, [&](int i) { return fabs(res[n + 2 * m + 2 * p + i]); });
+    double y1 = scope_sum(ctx, m, [&](int i) { return fabs(y[i]); });
+    double z1 = scope_sum(ctx, p, [&](int i) { return fabs(z[i]); });
+    double t1 = scope_sum(ctx, p, [&](int i) { return fabs(t[i]); });
+    if (ctx.tid == 0) {
+        double sd = (m + p) > 0 ? fmax(100.0, (y1 + z1) / (double)(m + p)) / 100.0 : 1.0;
+        double sc = p > 0 ? fmax(100.0, t1 / (double)p) / 100.0 : 1.0;
+        I.scal[S_RESIDUAL_VIOLATION] = r1 / (double)P.total;
+        I.scal[S_OPTIMALITY_VIOLATION] = fmax(fmax(lag / sd, eq), fmax(cn, cp / sc));
+        I.scal[S_SLACK_VIOLATION] = fmax(eq, cn);
+    }
+    ctx.sync();
+}
+
+// theta = ||[g - r; h - s]||_1 / (m + p) at point w (constraint_violation.jl:1-13)
+CB_DEV double constraint_violation(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *w)
+{
+    const double *r = w + P.n, *s = w + P.n + P.m;
+    double a = scope_sum(ctx, P.m, [&](int i) { return fabs(I.g[i] - r[i]); });
+    double b = scope_sum(ctx, P.p, [&](int i) { return fabs(I.h[i] - s[i]); });
+    return (a + b) / (double)(P.m + P.p);
+}
+
+// M = f + lambda'r + rho/2 r'r - kappa Phi at point w (merit.jl:2-15)
+CB_DEV double merit_value(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *w)
+{
+    const double *r = w + P.n;
+    double lr = scope_sum(ctx, P.m, [&](int i) { return I.lambda[i] * r[i]; });
+    double rr = scope_sum(ctx, P.m, [&](int i) { return r[i] * r[i]; });
+    double M = 0.0;
+    M += I.scal[S_OBJECTIVE];
+    M += lr + 0.5 * I.scal[S_RHO] * rr;
+    M -= I.scal[S_KAPPA] * I.scal[S_BARRIER];
+    return M;
+}
+
+CB_DEV void merit_gradient(const Ctx &ctx, const DevProblem &P, const Inst &I)
+{   // merit.jl:17-31
+    const double *r = I.w + P.n;
+    const double rho = I.scal[S_RHO], kappa = I.scal[S_KAPPA];
+    PAR_FOR(i, P.n) I.mgrad[i] = I.grad[i];
+    PAR_FOR(i, P.m) I.mgrad[P.n + i] = I.lambda[i] + rho * r[i];
+    PAR_FOR(i, P.p) I.mgrad[P.n + P.m + i] = -1.0 * kappa * I.bgrad[i];
+    ctx.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ KKT assembly
+// Writes the upper triangle of the reduced matrix K straight into the (zeroed) supernodal
+// panels.  eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.
+CB_DEVN void kkt_assemble(const Ctx &ctx, const DevProblem &P, const Inst &I)
+{
+    const double ep = I.scal[S_EPSP], ed = I.scal[S_EPSD], rho = I.scal[S_RHO];
+    const double *s = I.w + P.n + P.m, *t = I.w + P.n + 2 * P.m + 2 * P.p;
+    double *pan = I.panels;
+    {   // zero (two doubles per store; panel_total is even)
+        long long n2 = P.panel_total / 2;
+#if CB_ON_DEVICE
+        double2 *p2 = reinterpret_cast<double2 *>(pan);
+        for (long long i = ctx.tid; i < n2; i += ctx.nthr) p2[i] = make_double2(0.0, 0.0);
+#else
+        for (long long i = 0; i < 2 * n2; i++) pan[i] = 0.0;
+#endif
+    }
+    ctx.sync();
+    PAR_FOR(k, P.nnzW) pan[P.dW[k]] = I.Wv[k];
+    PAR_FOR(k, P.nnzG) pan[P.dG[k]] = I.Gv[k];
+    PAR_FOR(k, P.nnzC) pan[P.dC[k]] = I.Cv[k];
+    const double Jrr = rho + ep, Jyy = -ed, Jzz = -ed, Jss = ep;
+    PAR_FOR(i, P.m) pan[P.dY[i]] = -1.0 / Jrr + Jyy;
+    PAR_FOR(i, P.q_nn) {
+        double Sb = s[i] - ed, Ti = t[i];
+        pan[P.dZnn[i]] = -1.0 * Sb / (Ti + Sb * Jss) + Jzz;
+    }
+    ctx.sync();
+    PAR_FOR(j, P.n) pan[P.dW[P.Wdiag[j]]] += ep;
+    // SOC blocks: column j (rows i <= j) of -(arrow(u))^-1 Sbar + D, u = first row of T + Sbar*P
+    PAR_FOR(k, P.nsoc) {
+        int d = P.soc_dims[k];
+        const double *sk = s + P.soc_off[k], *tk = t + P.soc_off[k];
+        const long long *dst = P.dZsoc + P.soc_tri[k];
+        auto u = [&](int i) { return i == 0 ? tk[0] + (sk[0] - ed) * Jss : tk[i] + sk[i] * Jss; };
+        int tri = 0;
+        for (int j = 0; j < d; j++) {
+            auto x = [&](int i) {   // column j of Sbar = arrow(s) - eps_d I
+                if (j == 0) return i == 0 ? sk[0] - ed : sk[i];
+                return i == 0 ? sk[j] : (i == j ? sk[0] - ed : 0.0);
+            };
+            soc_arrow_inverse(d, u, x, [&](int i, double v) {
+                if (i <= j) {
+                    double e = 0.0;
+                    e -= v;
+                    if (i == j) e += Jzz;
+                    pan[dst[tri + i]] = e;
+                }
+            });
+            tri += j + 1;
+        }
+    }
+    ctx.sync();
+}
+
+// generic-matrix mode (LinearSolver seam): scatter the caller's upper-triangle values
+CB_DEVN void matrix_assemble(const Ctx &ctx, const DevProblem &P, double *pan, const double *Ax)
+{
+    long long n2 = P.panel_total / 2;
+#if CB_ON_DEVICE
+    double2 *p2 = reinterpret_cast<double2 *>(pan);
+    for (long long i = ctx.tid; i < n2; i += ctx.nthr) p2[i] = make_double2(0.0, 0.0);
+#else
+    for (long long i = 0; i < 2 * n2; i++) pan[i] = 0.0;
+#endif
+    ctx.sync();
+    PAR_FOR(k, P.nnzA) pan[P.dA[k]] = Ax[k];
+    ctx.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ supernodal LDL^T
+// One supernode: pull the updates of its descendants, then factor the (nrow x w) panel in place.  Scope = the
+// threads in ctx (a warp or the CTA).  Unscaled columns are kept until the end so that each pivot step needs one
+// barrier; the final pass divides by the pivots (L = A D^-1) and publishes D, 1/D.
+CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, int s)
+{
+    const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+    const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
+    double *Ps = pan + P.panel_off[s];
+    for (int q = P.upd_ptr[s]; q < P.upd_ptr[s + 1]; q++) {
+        const UpdateEntry u = P.upd[q];
+        const int cd0 = P.sn_start[u.d], wd = P.sn_start[u.d + 1] - cd0;
+        const int nRd = P.rows_ptr[u.d + 1] - P.rows_ptr[u.d], nrowd = wd + nRd;
+        const double *Pd = pan + P.panel_off[u.d] + wd + u.a;   // first contributing row of d
+        const double *Dd = D + cd0;
+        const int *rel = P.rel + u.rel;
+        const int nt = nRd - u.a, nb = u.b - u.a;
+        PAR_FOR(e, nt * nb) {
+            int i = e % nt, j = e / nt;
+            if (i >= j) {
+                double acc = 0.0;
+                for (int k = 0; k < wd; k++) acc += Pd[i + (long long)k * nrowd] * (Pd[j + (long long)k * nrowd] * Dd[k]);
+                Ps[rel[i] + (long long)rel[j] * nrow] -= acc;
+            }
+        }
+        ctx.sync();
+    }
+    for (int k = 0; k < w; k++) {
+        ctx.sync();
+        const double dk = Ps[k + (long long)k * nrow];
+        const double dinv = dk != 0.0 ? 1.0 / dk : 0.0;
+        const int ncol = w - 1 - k;
+        PAR_FOR(e, ncol * nrow) {
+            int j = k + 1 + e / nrow, i = e % nrow;
+            if (i >= j) Ps[i + (long long)j * nrow] -= Ps[i + (long long)k * nrow] * (Ps[j + (long long)k * nrow] * dinv);
+        }
+    }
+    ctx.sync();
+    PAR_FOR(e, w * nrow) {
+        int k = e / nrow, i = e % nrow;
+        if (i > k) {
+            double dk = Ps[k + (long long)k * nrow];
+            Ps[i + (long long)k * nrow] *= (dk != 0.0 ? 1.0 / dk : 0.0);
+        }
+    }
+    PAR_FOR(k, w) {
+        double dk = Ps[k + (long long)k * nrow];
+        D[c0 + k] = dk;
+        Dinv[c0 + k] = dk != 0.0 ? 1.0 / dk : 0.0;
+    }
+    ctx.sync();
+}
+
+#if CB_ON_DEVICE
+#define CB_WARP_ID (threadIdx.x >> 5)
+#define CB_NUM_WARPS ((blockDim.x + 31) >> 5)
+#define CB_CTA_SYNC() __syncthreads()
+#else
+#define CB_WARP_ID 0
+#define CB_NUM_WARPS 1
+#define CB_CTA_SYNC()
+#endif
+
+// run f(scope, supernode) over the level schedule (forward = leaves first)
+template <class F> CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward, F f)
+{
+    Ctx wctx = cta;
+#if CB_ON_DEVICE
+    wctx.tid = threadIdx.x & 31;
+    wctx.nthr = 32;
+    wctx.warp_scope = 1;
+#endif
+    for (int pi = 0; pi < P.nphases; pi++) {
+        const Phase ph = P.phases[forward ? pi : P.nphases - 1 - pi];
+        if (ph.mode == 1) {
+            for (int q = ph.begin; q < ph.end; q++) f(cta, P.order[q]);
+        } else {
+            for (int q = ph.begin + CB_WARP_ID; q < ph.end; q += CB_NUM_WARPS) f(wctx, P.order[q]);
+        }
+        CB_CTA_SYNC();
+    }
+}
+
+// numeric factorisation + inertia (positive = #(D>0), negative = #(D<=0), zero = #(D==0); linear_solver.jl:33-44)
+CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, int *istat)
+{
+    for_each_supernode(ctx, P, true, [&](const Ctx &c, int s) { factor_supernode(c, P, pan, D, Dinv, s); });
+    double pos = scope_sum(ctx, P.N, [&](int i) { return D[i] > 0.0 ? 1.0 : 0.0; });
+    double zer = scope_sum(ctx, P.N, [&](int i) { return D[i] == 0.0 ? 1.0 : 0.0; });
+    if (ctx.tid == 0) {
+        istat[I_INERTIA_POS] = (int)pos;
+        istat[I_INERTIA_NEG] = P.N - (int)pos;
+        istat[I_INERTIA_ZERO] = (int)zer;
+        istat[I_FACTORIZATIONS]++;
+    }
+    ctx.sync();
+}
+
+// x = P' L^-T D^-1 L^-1 P b; b and x are in natural order (may alias), xp is an N-vector of scratch
+CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, const double *Dinv, const double *b,
+                       double *x, double *xp, int *istat)
+{
+    PAR_FOR(k, P.N) xp[k] = b[P.perm[k]];
+    ctx.sync();
+    // forward: pull from descendants through the per-column row lists, then the unit-lower diagonal block
+    for_each_supernode(ctx, P, true, [&](const Ctx &c, int s) {
+        const Ctx &ctx = c;
+        const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+        const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
+        const double *Ps = pan + P.panel_off[s];
+        PAR_FOR(j, w) {
+            double acc = 0.0;
+            for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
+                const int d = P.fwd_d[q], cd0 = P.sn_start[d], wd = P.sn_start[d + 1] - cd0;
+                const int nrowd = wd + (P.rows_ptr[d + 1] - P.rows_ptr[d]);
+                const double *Ld = pan + P.panel_off[d] + P.fwd_row[q];
+                for (int k = 0; k < wd; k++) acc += Ld[(long long)k * nrowd] * xp[cd0 + k];
+            }
+            xp[c0 + j] -= acc;
+        }
+        for (int k = 0; k + 1 < w; k++) {
+            ctx.sync();
+            const double xk = xp[c0 + k];
+            PAR_FOR(i, w - 1 - k) xp[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
+        }
+        ctx.sync();
+    });
+    PAR_FOR(k, P.N) xp[k] *= Dinv[k];
+    ctx.sync();
+    // backward: gather from the ancestors' (already final) entries, then the unit-upper diagonal block
+    for_each_supernode(ctx, P, false, [&](const Ctx &c, int s) {
+        const Ctx &ctx = c;
+        const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+        const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
+        const double *Ps = pan + P.panel_off[s];
+        const int *R = P.rows + P.rows_ptr[s];
+        PAR_FOR(k, w) {
+            double acc = 0.0;
+            const double *col = Ps + (long long)k * nrow + w;
+            for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
+            xp[c0 + k] -= acc;
+        }
+        for (int k = w - 1; k > 0; k--) {
+            ctx.sync();
+            const double xk = xp[c0 + k];
+            PAR_FOR(i, k) xp[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
+        }
+        ctx.sync();
+    });
+    PAR_FOR(k, P.N) x[P.perm[k]] = xp[k];
+    if (ctx.tid == 0 && istat) istat[I_SOLVES]++;
+    ctx.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ reduced rhs / recovery
+CB_DEVN void reduced_rhs(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *res, double *rs)
+{
+    const int n = P.n, m = P.m, p = P.p;
+    const double ep = I.scal[S_EPSP], ed = I.scal[S_EPSD], rho = I.scal[S_RHO];
+    const double Jrr = rho + ep, Jss = ep;
+    const double *s = I.w + n + m, *t = I.w + n + 2 * m + 2 * p;
+    const double *rr = res + n, *rsl = res + n + m, *ry = res + n + m + p, *rz = res + n + 2 * m + p,
+                 *rt = res + n + 2 * m + 2 * p;
+    PAR_FOR(i, n) rs[i] = res[i];
+    PAR_FOR(i, m) rs[n + i] = ry[i] + rr[i] / Jrr;
+    PAR_FOR(i, P.q_nn) {
+        double Sb = s[i] - ed, Ti = t[i];
+        rs[n + m + i] = rz[i] + (rt[i] + Sb * rsl[i]) / (Ti + Sb * Jss);
+    }
+    PAR_FOR(k, P.nsoc) {
+        int d = P.soc_dims[k], c0 = P.soc_off[k];
+        if (d > 0) {
+            const double *sk = s + c0, *tk = t + c0, *a = rsl + c0, *b = rt + c0;
+            auto u = [&](int i) { return i == 0 ? tk[0] + (sk[0] - ed) * Jss : tk[i] + sk[i] * Jss; };
+            double dot = 0.0;   // first row of Sbar times rs
+            for (int i = 0; i < d; i++) dot += (i == 0 ? sk[0] - ed : sk[i]) * a[i];
+            auto x = [&](int i) { return (i == 0 ? dot : (sk[0] - ed) * a[i] + a[0] * sk[i]) + b[i]; };
+            soc_arrow_inverse(d, u, x, [&](int i, double v) { rs[n + m + c0 + i] = rz[c0 + i] + v; });
+        }
+    }
+    ctx.sync();
+}
+
+CB_DEVN void recover_step(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *res, const double *xs,
+                          double *step)
+{
+    const int n = P.n, m = P.m, p = P.p;
+    const double ep = I.scal[S_EPSP], ed = I.scal[S_EPSD], rho = I.scal[S_RHO];
+    const double Jrr = rho + ep, Jss = ep;
+    const double *s = I.w + n + m, *t = I.w + n + 2 * m + 2 * p;
+    const double *rr = res + n, *rsl = res + n + m, *rt = res + n + 2 * m + 2 * p;
+    const double *dy = xs + n, *dz = xs + n + m;
+    double *dr = step + n, *ds = step + n + m, *dt = step + n + 2 * m + 2 * p;
+    PAR_FOR(i, n) step[i] = xs[i];
+    PAR_FOR(i, m) {
+        step[n + m + p + i] = dy[i];
+        dr[i] = (rr[i] + dy[i]) / Jrr;
+    }
+    PAR_FOR(i, p) step[n + 2 * m + p + i] = dz[i];
+    PAR_FOR(i, P.q_nn) {
+        double Sb = s[i] - ed, Ti = t[i];
+        double dsi = (rt[i] + Sb * (rsl[i] + dz[i])) / (Ti + Sb * Jss);
+        ds[i] = dsi;
+        dt[i] = (rt[i] - Ti * dsi) / Sb;
+    }
+    PAR_FOR(k, P.nsoc) {
+        int d = P.soc_dims[k], c0 = P.soc_off[k];
+        if (d > 0) {
+            const double *sk = s + c0, *tk = t + c0, *a = rsl + c0, *b = rt + c0, *z = dz + c0;
+            double *dsk = ds + c0, *dtk = dt + c0;
+            auto sb = [&](int i) { return i == 0 ? sk[0] - ed : sk[i]; };           // first row of Sbar
+            auto u = [&](int i) { return i == 0 ? tk[0] + (sk[0] - ed) * Jss : tk[i] + sk[i] * Jss; };
+            double dot = 0.0;
+            for (int i = 0; i < d; i++) dot += sb(i) * (a[i] + z[i]);
+            auto x = [&](int i) {
+                double v = i == 0 ? dot : (sk[0] - ed) * (a[i] + z[i]) + (a[0] + z[0]) * sk[i];
+                return b[i] + v;
+            };
+            soc_arrow_inverse(d, u, x, [&](int i, double v) { dsk[i] = v; });
+            double dot2 = 0.0;   // first row of arrow(t) times ds
+            for (int i = 0; i < d; i++) dot2 += tk[i] * dsk[i];
+            auto x2 = [&](int i) { return b[i] - (i == 0 ? dot2 : tk[0] * dsk[i] + dsk[0] * tk[i]); };
+            soc_arrow_inverse(d, sb, x2, [&](int i, double v) { dtk[i] = v; });
+        }
+    }
+    ctx.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ J * v (matrix-free)
+CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *v, double *out)
+{
+    const int n = P.n, m = P.m, p = P.p;
+    const double ep = I.scal[S_EPSP], ed = I.scal[S_EPSD], rho = I.scal[S_RHO];
+    const double *s = I.w + n + m, *t = I.w + n + 2 * m + 2 * p;
+    const double *vx = v, *vr = v + n, *vs = v + n + m, *vy = v + n + m + p, *vz = v + n + 2 * m + p,
+                 *vt = v + n + 2 * m + 2 * p;
+    PAR_FOR(i, n) {
+        double a = ep * vx[i];
+        for (int k = P.Wfull.ptr[i]; k < P.Wfull.ptr[i + 1]; k++) a += I.Wv[P.Wfull.src[k]] * vx[P.Wfull.col[k]];
+        for (int k = P.Gp[i]; k < P.Gp[i + 1]; k++) a += I.Gv[k] * vy[P.Gi[k]];
+        for (int k = P.Cp[i]; k < P.Cp[i + 1]; k++) a += I.Cv[k] * vz[P.Ci[k]];
+        out[i] = a;
+    }
+    PAR_FOR(i, m) {
+        out[n + i] = (rho + ep) * vr[i] - vy[i];
+        double a = 0.0;
+        for (int k = P.Grow.ptr[i]; k < P.Grow.ptr[i + 1]; k++) a += I.Gv[P.Grow.src[k]] * vx[P.Grow.col[k]];
+        out[n + m + p + i] = a - vr[i] - ed * vy[i];
+    }
+    PAR_FOR(i, p) {
+        out[n + m + i] = ep * vs[i] - vz[i] - vt[i];
+        double a = 0.0;
+        for (int k = P.Crow.ptr[i]; k < P.Crow.ptr[i + 1]; k++) a += I.Cv[P.Crow.src[k]] * vx[P.Crow.col[k]];
+        out[n + 2 * m + p + i] = a - vs[i] - ed * vz[i];
+    }
+    PAR_FOR(i, P.q_nn) out[n + 2 * m + 2 * p + i] = t[i] * vs[i] + (s[i] - ed) * vt[i];
+    PAR_FOR(k, P.nsoc) {
+        int d = P.soc_dims[k], c0 = P.soc_off[k];
+        const double *sk = s + c0, *tk = t + c0, *a = vs + c0, *b = vt + c0;
+        double dt_ = 0.0, dsb = 0.0;
+        for (int i = 0; i < d; i++) { dt_ += tk[i] * a[i]; dsb += sk[i] * b[i]; }
+        for (int i = 0; i < d; i++)
+            out[n + 2 * m + 2 * p + c0 + i] = arrow_apply(tk, a, i, dt_) + arrow_apply(sk, b, i, dsb) - ed * b[i];
+    }
+    ctx.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ search direction
+// factorize_regularized_residual_jacobian_variables!  inertia.jl:13-28
+CB_DEV bool factorize_regularized(const Ctx &ctx, const DevProblem &P, const Inst &I)
+{
+    kkt_assemble(ctx, P, I);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.istat);
+    bool ok = I.istat[I_INERTIA_POS] == P.n && I.istat[I_INERTIA_NEG] == P.m + P.p && I.istat[I_INERTIA_ZERO] == 0;
+    ctx.sync();
+    if (ctx.tid == 0) I.istat[I_TRIALS]++;
+    ctx.sync();
+    return ok;
+}
+
+// inertia_correction!  inertia.jl:30-79.  All threads follow the same (uniform) control flow.
+CB_DEVN int inertia_correction(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o)
+{
+    if (ctx.tid == 0) {
+        I.scal[S_EPSP] = o.primal_regularization_initial;
+        I.scal[S_EPSD] = o.dual_regularization_initial;
+        I.istat[I_TRIALS] = 0;
+    }
+    ctx.sync();
+    if (factorize_regularized(ctx, P, I)) return ST_OK;   // IC-1
+    if (ctx.tid == 0) {
+        if (I.istat[I_INERTIA_ZERO] != 0)                  // IC-2
+            I.scal[S_EPSD] = o.dual_regularization * pow(I.scal[S_KAPPA], o.dual_regularization_exponent);
+        // IC-3: the reference's `primal_regularization_last == 0.0` compares a Vector with a Float64 (always false)
+        double v = o.scaling_regularization_last * I.scal[S_EPSP_LAST];
+        I.scal[S_EPSP] = o.min_regularization > v ? o.min_regularization : v;
+    }
+    ctx.sync();
+    for (;;) {
+        if (factorize_regularized(ctx, P, I)) break;      // IC-4
+        double ep = I.scal[S_EPSP];
+        ep = (I.scal[S_EPSP_LAST] == 0.0 ? o.scaling_regularization_initial : o.scaling_regularization) * ep;   // IC-5
+        ctx.sync();
+        if (ctx.tid == 0) I.scal[S_EPSP] = ep;
+        ctx.sync();
+        if (ep > o.max_regularization) return ST_INERTIA_FAILURE;   // IC-6
+    }
+    if (ctx.tid == 0) I.scal[S_EPSP_LAST] = I.scal[S_EPSP];
+    ctx.sync();
+    return ST_OK;
+}
+
+// search_direction_symmetric!  search_direction.jl:25-104 (the redundant re-factorisation of linear_solve! is skipped,
+// SURVEY.md Appendix A.7)
+CB_DEV void direction_symmetric(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *res, double *step)
+{
+    reduced_rhs(ctx, P, I, res, I.rs);
+    ldl_solve(ctx, P, I.panels, I.Dinv, I.rs, I.xs, I.xp, I.istat);
+    recover_step(ctx, P, I, res, I.xs, step);
+}
+
+CB_DEV double residual_error(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *step)
+{   // err = R - J step, returns its infinity norm
+    jacobian_times(ctx, P, I, step, I.tmp);
+    PAR_FOR(i, P.total) I.err[i] = I.res[i] - I.tmp[i];
+    ctx.sync();
+    return scope_max(ctx, P.total, [&](int i) { return fabs(I.err[i]); });
+}
+
+// iterative_refinement!  iterative_refinement.jl:1-53
+CB_DEVN bool iterative_refinement(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o)
+{
+    int iteration = 0;
+    double rn = residual_error(ctx, P, I, I.step);
+    const double rn0 = rn;
+    bool done = false;
+    while (iteration <= o.max_iterative_refinement) {
+        if (rn <= o.iterative_refinement_tolerance && iteration >= o.min_iterative_refinement) { done = true; break; }
+        direction_symmetric(ctx, P, I, I.err, I.corr);
+        PAR_FOR(i, P.total) I.step[i] += I.corr[i];
+        ctx.sync();
+        rn = residual_error(ctx, P, I, I.step);
+        iteration++;
+    }
+    if (ctx.tid == 0) {
+        I.istat[I_REFINE] = iteration;
+        I.scal[S_REFINE_NORM] = rn;
+        I.scal[S_REFINE_NORM_INITIAL] = rn0;
+    }
+    ctx.sync();
+    return done || rn <= rn0;
+}
+
+// Fallback when refinement fails.  The reference re-solves J step = R with UMFPACK (search_direction.jl:22,113); here
+// the same system is solved by restarted GMRES on the matrix-free J, right-preconditioned with the reduced LDL^T
+// solve + recovery (the linear map the refinement also uses).  Starts from zero like a direct solve.
+CB_DEVN bool gmres_fallback(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o)
+{
+    const int T = P.total, mr = o.gmres_restart;
+    double *V = I.krylov;            // (mr+1) x T
+    double *H = V + (long long)(mr + 1) * T;   // (mr+1) x mr column-major Hessenberg, then cs[mr], sn[mr], g[mr+1], y[mr]
+    double *cs = H + (mr + 1) * mr, *sn = cs + mr, *g = sn + mr, *y = g + mr + 1;
+    PAR_FOR(i, T) I.step[i] = 0.0;
+    ctx.sync();
+    int total_it = 0;
+    bool ok = false;
+    double rn = 0.0;
+    for (int cycle = 0; cycle < o.gmres_max_cycles; cycle++) {
+        rn = residual_error(ctx, P, I, I.step);     // err = R - J step
+        if (rn <= o.iterative_refinement_tolerance) { ok = true; break; }
+        double beta = sqrt(scope_sum(ctx, T, [&](int i) { return I.err[i] * I.err[i]; }));
+        PAR_FOR(i, T) V[i] = I.err[i] / beta;
+        if (ctx.tid == 0) { for (int k = 0; k <= mr; k++) g[k] = 0.0; g[0] = beta; }
+        ctx.sync();
+        int j = 0;
+        for (; j < mr; j++) {
+            double *vj = V + (long long)j * T, *wv = V + (long long)(j + 1) * T;
+            direction_symmetric(ctx, P, I, vj, I.corr);      // z = M^-1 v_j
+            jacobian_times(ctx, P, I, I.corr, wv);           // w = J z
+            for (int i = 0; i <= j; i++) {                   // modified Gram-Schmidt
+                const double *vi = V + (long long)i * T;
+                double h = scope_sum(ctx, T, [&](int k) { return wv[k] * vi[k]; });
+                PAR_FOR(k, T) wv[k] -= h * vi[k];
+                if (ctx.tid == 0) H[i + j * (mr + 1)] = h;
+                ctx.sync();
+            }
+            double hn = sqrt(scope_sum(ctx, T, [&](int k) { return wv[k] * wv[k]; }));
+            PAR_FOR(k, T) wv[k] = hn > 0.0 ? wv[k] / hn : 0.0;
+            if (ctx.tid == 0) {
+                H[j + 1 + j * (mr + 1)] = hn;
+                for (int i = 0; i < j; i++) {                // apply previous rotations
+                    double a = H[i + j * (mr + 1)], b = H[i + 1 + j * (mr + 1)];
+                    H[i + j * (mr + 1)] = cs[i] * a + sn[i] * b;
+                    H[i + 1 + j * (mr + 1)] = -sn[i] * a + cs[i] * b;
+                }
+                double a = H[j + j * (mr + 1)], b = H[j + 1 + j * (mr + 1)];
+                double r = sqrt(a * a + b * b);
+                cs[j] = r > 0.0 ? a / r : 1.0;
+                sn[j] = r > 0.0 ? b / r : 0.0;
+                H[j + j * (mr + 1)] = r;
+                H[j + 1 + j * (mr + 1)] = 0.0;
+                g[j + 1] = -sn[j] * g[j];
+                g[j] = cs[j] * g[j];
+            }
+            ctx.sync();
+            total_it++;
+            double est = fabs(g[j + 1]);
+            ctx.sync();
+            if (est <= 0.1 * o.iterative_refinement_tolerance || hn == 0.0) { j++; break; }
+        }
+        if (ctx.tid == 0) {                                   // back substitution
+            for (int i = j - 1; i >= 0; i--) {
+                double a = g[i];
+                for (int k = i + 1; k < j; k++) a -= H[i + k * (mr + 1)] * y[k];
+                y[i] = a / H[i + i * (mr + 1)];
+            }
+        }
+        ctx.sync();
+        PAR_FOR(k, T) {                                       // tmp = V y
+            double a = 0.0;
+            for (int i = 0; i < j; i++) a += V[(long long)i * T + k] * y[i];
+            I.tmp[k] = a;
+        }
+        ctx.sync();
+        PAR_FOR(k, T) I.err[k] = I.tmp[k];
+        ctx.sync();
+        direction_symmetric(ctx, P, I, I.err, I.corr);        // step += M^-1 (V y)
+        PAR_FOR(k, T) I.step[k] += I.corr[k];
+        ctx.sync();
+    }
+    if (!ok) {
+        rn = residual_error(ctx, P, I, I.step);
+        ok = rn <= o.iterative_refinement_tolerance;
+    }
+    if (ctx.tid == 0) { I.istat[I_GMRES_ITERS] = total_it; I.scal[S_REFINE_NORM] = rn; }
+    ctx.sync();
+    return ok;
+}
+
+// search_direction!  search_direction.jl:1-23
+CB_DEVN int search_direction(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o)
+{
+    int st = inertia_correction(ctx, P, I, o);
+    if (st != ST_OK) return st;
+    direction_symmetric(ctx, P, I, I.res, I.step);
+    if (ctx.tid == 0) { I.istat[I_REFINE_OK] = 1; I.istat[I_USED_FALLBACK] = 0; I.istat[I_REFINE] = 0; }
+    ctx.sync();
+    if (o.iterative_refinement) {
+        bool ok = iterative_refinement(ctx, P, I, o);
+        if (ctx.tid == 0) I.istat[I_REFINE_OK] = ok ? 1 : 0;
+        ctx.sync();
+        if (!ok) {
+            if (I.krylov == nullptr) return ST_REFINEMENT_FAILURE;
+            bool gok = gmres_fallback(ctx, P, I, o);
+            if (ctx.tid == 0) { I.istat[I_USED_FALLBACK] = 1; I.istat[I_FALLBACKS]++; }
+            ctx.sync();
+            if (!gok) return ST_REFINEMENT_FAILURE;
+        }
+    }
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cone line search
+// cone_violation(xhat, x, tau), cones/cone.jl:62-68 with xhat = x - alpha * dx formed on the fly
+CB_DEV int cone_violation_step(const Ctx &ctx, const DevProblem &P, const double *x, const double *dx, double alpha,
+                               double tau, double *xhat)
+{
+    PAR_FOR(i, P.p) xhat[i] = x[i] - alpha * dx[i];
+    ctx.sync();
+    int nn = scope_any(ctx, P.q_nn, [&](int i) { return xhat[i] <= (1.0 - tau) * x[i]; });
+    int so = scope_any(ctx, P.nsoc, [&](int k) {
+        int d = P.soc_dims[k], c0 = P.soc_off[k];
+        if (d <= 0) return false;
+        double acc = 0.0;
+        for (int i = 1; i < d; i++) {
+            double v = xhat[c0 + i] - (1.0 - tau) * x[c0 + i];
+            acc += v * v;
+        }
+        return xhat[c0] - (1.0 - tau) * x[c0] <= sqrt(acc);
+    });
+    return nn | so;
+}
+
+// solve.jl:190-221: independent halving searches for s (step_size) and t (step_size_cone_slack_dual)
+CB_DEVN int cone_search(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o)
+{
+    const int os = P.n + P.m, ot = P.n + 2 * P.m + 2 * P.p;
+    const double tau = I.scal[S_TAU];
+    double a = 1.0, at = 1.0;
+    int it = 0, status = ST_OK;
+    while (cone_violation_step(ctx, P, I.w + os, I.step + os, a, tau, I.cand + os)) {
+        a = o.scaling_line_search * a;
+        it++;
+        if (it > o.max_cone_line_search) { status = ST_CONE_SEARCH_FAILURE; break; }
+    }
+    int ks = it;
+    it = 0;
+    if (status == ST_OK)
+        while (cone_violation_step(ctx, P, I.w + ot, I.step + ot, at, tau, I.cand + ot)) {
+            at = o.scaling_line_search * at;
+            it++;
+            if (it > o.max_cone_line_search) { status = ST_CONE_SEARCH_FAILURE; break; }
+        }
+    if (ctx.tid == 0) {
+        I.scal[S_STEP_SIZE] = a;
+        I.scal[S_STEP_SIZE_T] = at;
+        I.istat[I_KS] = ks;
+        I.istat[I_KT] = it;
+    }
+    ctx.sync();
+    return status;
+}
+
+}  // namespace cb200

@@ -1,0 +1,149 @@
+// host_setup.h -- host-side construction of the shared (per-pattern) problem description: cone layout, row views of
+// W/G/C, the pattern of the reduced KKT matrix K in the reference's (x, y, z) order
+// (src/solver/residual_jacobian_variables.jl:110-167, upper triangle as kept by triu!, linear_solver.jl:23), its
+// symbolic factorisation and the assembly destinations.  Pure C++; api.cu uploads the vectors to the device.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "device_core.h"
+#include "symbolic.h"
+
+namespace cb200 {
+
+struct HostProblem {
+    int n = 0, m = 0, p = 0, N = 0, total = 0, q_nn = 0, nsoc = 0, tri_total = 0, nnzW = 0, nnzG = 0, nnzC = 0;
+    std::vector<int> soc_off, soc_d, soc_tri, Wp, Wi, Wdiag, Wfp, Wfc, Wfs, Gp, Gi, Cp, Ci, Grp, Gcj, Gsrc, Crp, Ccj,
+        Csrc, Kp, Ki;
+    std::vector<long long> dW, dG, dC, dY, dZnn, dZsoc;
+    Symbolic sym;
+
+    static void csr_view(int nrows, int ncols, const int *cp, const int *ri, std::vector<int> &rp, std::vector<int> &cj,
+                         std::vector<int> &src)
+    {
+        int nnz = cp[ncols];
+        rp.assign(nrows + 1, 0);
+        cj.assign(nnz, 0);
+        src.assign(nnz, 0);
+        for (int k = 0; k < nnz; k++) rp[ri[k] + 1]++;
+        for (int i = 0; i < nrows; i++) rp[i + 1] += rp[i];
+        std::vector<int> nx(rp.begin(), rp.end() - 1);
+        for (int j = 0; j < ncols; j++)
+            for (int k = cp[j]; k < cp[j + 1]; k++) {
+                cj[nx[ri[k]]] = j;
+                src[nx[ri[k]]] = k;
+                nx[ri[k]]++;
+            }
+    }
+
+    // returns "" or an error message
+    std::string build(int n_, int m_, int p_, int q_nn_, int nsoc_, const int *soc_dims, const int *Wp_, const int *Wi_,
+                      const int *Gp_, const int *Gi_, const int *Cp_, const int *Ci_, const int *perm, int big_threshold)
+    {
+        n = n_; m = m_; p = p_; N = n + m + p; total = n + 2 * m + 3 * p; q_nn = q_nn_; nsoc = nsoc_;
+        if (n <= 0 || m < 0 || p < 0 || q_nn < 0 || nsoc < 0) return "invalid dimensions";
+        nnzW = Wp_[n]; nnzG = Gp_[n]; nnzC = Cp_[n];
+        Wp.assign(Wp_, Wp_ + n + 1); Wi.assign(Wi_, Wi_ + nnzW);
+        Gp.assign(Gp_, Gp_ + n + 1); Gi.assign(Gi_, Gi_ + nnzG);
+        Cp.assign(Cp_, Cp_ + n + 1); Ci.assign(Ci_, Ci_ + nnzC);
+        soc_off.assign(nsoc, 0); soc_d.assign(soc_dims, soc_dims + nsoc); soc_tri.assign(nsoc, 0);
+        int off = q_nn, tri = 0;
+        for (int k = 0; k < nsoc; k++) {
+            if (soc_d[k] < 0) return "negative cone dimension";
+            soc_off[k] = off; soc_tri[k] = tri; off += soc_d[k]; tri += soc_d[k] * (soc_d[k] + 1) / 2;
+        }
+        if (off != p) return "cone dimensions do not sum to p";
+        tri_total = tri;
+        Wdiag.assign(n, -1);
+        for (int j = 0; j < n; j++)
+            for (int k = Wp[j]; k < Wp[j + 1]; k++) {
+                if (Wi[k] < 0 || Wi[k] > j) return "W must be given as its upper triangle";
+                if (Wi[k] == j) Wdiag[j] = k;
+            }
+        for (int j = 0; j < n; j++)
+            if (Wdiag[j] < 0) return "W pattern must contain every diagonal entry";
+        for (int k = 0; k < nnzG; k++) if (Gi[k] < 0 || Gi[k] >= m) return "G row index out of range";
+        for (int k = 0; k < nnzC; k++) if (Ci[k] < 0 || Ci[k] >= p) return "C row index out of range";
+        // symmetric W by rows
+        Wfp.assign(n + 1, 0);
+        for (int j = 0; j < n; j++)
+            for (int k = Wp[j]; k < Wp[j + 1]; k++) { Wfp[Wi[k] + 1]++; if (Wi[k] != j) Wfp[j + 1]++; }
+        for (int i = 0; i < n; i++) Wfp[i + 1] += Wfp[i];
+        Wfc.assign(Wfp[n], 0); Wfs.assign(Wfp[n], 0);
+        {
+            std::vector<int> nx(Wfp.begin(), Wfp.end() - 1);
+            for (int j = 0; j < n; j++)
+                for (int k = Wp[j]; k < Wp[j + 1]; k++) {
+                    int i = Wi[k];
+                    Wfc[nx[i]] = j; Wfs[nx[i]] = k; nx[i]++;
+                    if (i != j) { Wfc[nx[j]] = i; Wfs[nx[j]] = k; nx[j]++; }
+                }
+        }
+        csr_view(m, n, Gp.data(), Gi.data(), Grp, Gcj, Gsrc);
+        csr_view(p, n, Cp.data(), Ci.data(), Crp, Ccj, Csrc);
+        // pattern of K: W columns, rows of G + diagonal, rows of C + cone block (rows above the diagonal) + diagonal
+        std::vector<int> eW(nnzW), eG(nnzG), eC(nnzC), eY(m), eZnn(q_nn), eZsoc(tri);
+        Kp.assign(N + 1, 0);
+        Ki.clear();
+        for (int j = 0; j < n; j++) {
+            Kp[j] = (int)Ki.size();
+            for (int k = Wp[j]; k < Wp[j + 1]; k++) { eW[k] = (int)Ki.size(); Ki.push_back(Wi[k]); }
+        }
+        for (int i = 0; i < m; i++) {
+            Kp[n + i] = (int)Ki.size();
+            for (int k = Grp[i]; k < Grp[i + 1]; k++) { eG[Gsrc[k]] = (int)Ki.size(); Ki.push_back(Gcj[k]); }
+            eY[i] = (int)Ki.size(); Ki.push_back(n + i);
+        }
+        {
+            int sk = 0, t = 0;
+            for (int i = 0; i < p; i++) {
+                Kp[n + m + i] = (int)Ki.size();
+                for (int k = Crp[i]; k < Crp[i + 1]; k++) { eC[Csrc[k]] = (int)Ki.size(); Ki.push_back(Ccj[k]); }
+                if (i < q_nn) { eZnn[i] = (int)Ki.size(); Ki.push_back(n + m + i); }
+                else {
+                    while (sk < nsoc && i >= soc_off[sk] + soc_d[sk]) sk++;
+                    // entries of column i: rows soc_off..i; stored per cone column by column (= soc_tri order)
+                    for (int r = soc_off[sk]; r <= i; r++) { eZsoc[t++] = (int)Ki.size(); Ki.push_back(n + m + r); }
+                }
+            }
+        }
+        Kp[N] = (int)Ki.size();
+        const char *msg = sym.analyze(N, Kp.data(), Ki.data(), perm, big_threshold);
+        if (msg[0]) return msg;
+        auto gather = [&](const std::vector<int> &e) {
+            std::vector<long long> d(e.size());
+            for (size_t k = 0; k < e.size(); k++) d[k] = sym.dest[e[k]];
+            return d;
+        };
+        dW = gather(eW); dG = gather(eG); dC = gather(eC); dY = gather(eY); dZnn = gather(eZnn); dZsoc = gather(eZsoc);
+        return "";
+    }
+};
+
+// Fill the pointer fields of a DevProblem from any provider `up(vector) -> const T*` (device upload or host data()).
+template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
+{
+    P.N = S.N; P.ns = S.ns; P.nphases = (int)S.phases.size(); P.max_w = S.max_w; P.max_nrow = S.max_nrow;
+    P.panel_total = S.panel_total;
+    P.perm = up(S.perm); P.sn_start = up(S.sn_start); P.rows_ptr = up(S.rows_ptr); P.rows = up(S.rows);
+    P.panel_off = up(S.panel_off); P.upd_ptr = up(S.upd_ptr); P.upd = up(S.upd); P.rel = up(S.rel);
+    P.order = up(S.order); P.phases = up(S.phases); P.fwd_ptr = up(S.fwd_ptr); P.fwd_d = up(S.fwd_d);
+    P.fwd_row = up(S.fwd_row);
+}
+
+template <class Up> void fill_problem(DevProblem &P, const HostProblem &H, Up up)
+{
+    P.n = H.n; P.m = H.m; P.p = H.p; P.total = H.total; P.q_nn = H.q_nn; P.nsoc = H.nsoc; P.tri_total = H.tri_total;
+    P.nnzW = H.nnzW; P.nnzG = H.nnzG; P.nnzC = H.nnzC;
+    fill_symbolic(P, H.sym, up);
+    P.soc_off = up(H.soc_off); P.soc_dims = up(H.soc_d); P.soc_tri = up(H.soc_tri);
+    P.Wp = up(H.Wp); P.Wi = up(H.Wi); P.Wdiag = up(H.Wdiag);
+    P.Wfull = Csr{up(H.Wfp), up(H.Wfc), up(H.Wfs)};
+    P.Gp = up(H.Gp); P.Gi = up(H.Gi); P.Cp = up(H.Cp); P.Ci = up(H.Ci);
+    P.Grow = Csr{up(H.Grp), up(H.Gcj), up(H.Gsrc)};
+    P.Crow = Csr{up(H.Crp), up(H.Ccj), up(H.Csrc)};
+    P.dW = up(H.dW); P.dG = up(H.dG); P.dC = up(H.dC); P.dY = up(H.dY); P.dZnn = up(H.dZnn); P.dZsoc = up(H.dZsoc);
+    P.dA = nullptr; P.nnzA = 0;
+}
+
+}  // namespace cb200

@@ -1,0 +1,362 @@
+// symbolic.cpp -- see symbolic.h
+#include "symbolic.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace cb200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Quotient-graph minimum degree (stand-in for AMD.amd, reference call site src/solver/qdldl.jl:135).
+// Variables keep a list of adjacent variables and adjacent elements; eliminating p creates element p whose boundary
+// is the union of p's variable neighbours and the boundaries of p's elements (which are absorbed).  Degrees of the
+// boundary variables are recomputed exactly with a stamped marker sweep.
+void minimum_degree(int n, const int *Ap, const int *Ai, std::vector<int> &perm)
+{
+    std::vector<std::vector<int>> adjV(n), adjE(n), elem(n);
+    for (int j = 0; j < n; j++)
+        for (int q = Ap[j]; q < Ap[j + 1]; q++) {
+            int i = Ai[q];
+            if (i == j) continue;
+            adjV[i].push_back(j);
+            adjV[j].push_back(i);
+        }
+    std::vector<int> status(n, 0);  // 0 variable, 1 element, 2 absorbed element
+    std::vector<int> degree(n), mark(n, -1);
+    for (int i = 0; i < n; i++) {
+        std::sort(adjV[i].begin(), adjV[i].end());
+        adjV[i].erase(std::unique(adjV[i].begin(), adjV[i].end()), adjV[i].end());
+        degree[i] = (int)adjV[i].size();
+    }
+    perm.assign(n, 0);
+    int stamp = 0;
+    std::vector<int> Lp;
+    for (int k = 0; k < n; k++) {
+        int p = -1;
+        for (int i = 0; i < n; i++)
+            if (status[i] == 0 && (p < 0 || degree[i] < degree[p])) p = i;
+        perm[k] = p;
+        // boundary of the new element
+        stamp++;
+        mark[p] = stamp;
+        Lp.clear();
+        for (int v : adjV[p])
+            if (status[v] == 0 && mark[v] != stamp) { mark[v] = stamp; Lp.push_back(v); }
+        for (int e : adjE[p]) {
+            if (status[e] != 1) continue;
+            for (int v : elem[e])
+                if (status[v] == 0 && mark[v] != stamp) { mark[v] = stamp; Lp.push_back(v); }
+            status[e] = 2;  // absorbed
+            std::vector<int>().swap(elem[e]);
+        }
+        status[p] = 1;
+        std::vector<int>().swap(adjV[p]);
+        std::vector<int>().swap(adjE[p]);
+        std::sort(Lp.begin(), Lp.end());
+        elem[p] = Lp;
+        // prune the boundary variables' lists: anything inside the new element is now represented by it
+        for (int i : Lp) {
+            auto &av = adjV[i];
+            size_t w = 0;
+            for (size_t r = 0; r < av.size(); r++)
+                if (status[av[r]] == 0 && mark[av[r]] != stamp) av[w++] = av[r];
+            av.resize(w);
+            auto &ae = adjE[i];
+            w = 0;
+            for (size_t r = 0; r < ae.size(); r++)
+                if (status[ae[r]] == 1 && ae[r] != p) ae[w++] = ae[r];
+            ae.resize(w);
+            ae.push_back(p);
+        }
+        // exact external degrees of the boundary variables
+        for (int i : Lp) {
+            stamp++;
+            mark[i] = stamp;
+            int cnt = 0;
+            for (int v : adjV[i])
+                if (mark[v] != stamp) { mark[v] = stamp; cnt++; }
+            for (int e : adjE[i])
+                for (int v : elem[e])
+                    if (status[v] == 0 && mark[v] != stamp) { mark[v] = stamp; cnt++; }
+            degree[i] = cnt;
+        }
+    }
+}
+
+// QDLDL_etree! (src/solver/qdldl.jl:358-395) on an upper-triangular CSC pattern; 0-based.
+static long long etree_counts(int n, const std::vector<int> &Up, const std::vector<int> &Ui, std::vector<int> &etree,
+                              std::vector<int> &Lnz)
+{
+    std::vector<int> work(n, -1);
+    etree.assign(n, -1);
+    Lnz.assign(n, 0);
+    for (int j = 0; j < n; j++) {
+        work[j] = j;
+        for (int q = Up[j]; q < Up[j + 1]; q++) {
+            int i = Ui[q];
+            while (work[i] != j) {
+                if (etree[i] < 0) etree[i] = j;
+                Lnz[i]++;
+                work[i] = j;
+                i = etree[i];
+            }
+        }
+    }
+    long long s = 0;
+    for (int i = 0; i < n; i++) s += Lnz[i];
+    return s;
+}
+
+// upper CSC (columns hold rows <= col, unsorted) of P A P' for elimination order perm
+static void permuted_upper(int n, const int *Ap, const int *Ai, const std::vector<int> &iperm, std::vector<int> &Up,
+                           std::vector<int> &Ui)
+{
+    Up.assign(n + 1, 0);
+    for (int j = 0; j < n; j++)
+        for (int q = Ap[j]; q < Ap[j + 1]; q++) {
+            int c = std::max(iperm[Ai[q]], iperm[j]);
+            Up[c + 1]++;
+        }
+    for (int j = 0; j < n; j++) Up[j + 1] += Up[j];
+    Ui.assign(Up[n], 0);
+    std::vector<int> next(Up.begin(), Up.end() - 1);
+    for (int j = 0; j < n; j++)
+        for (int q = Ap[j]; q < Ap[j + 1]; q++) {
+            int a = iperm[Ai[q]], b = iperm[j];
+            Ui[next[std::max(a, b)]++] = std::min(a, b);
+        }
+}
+
+const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold)
+{
+    N = n;
+    nnzA = Ap[n];
+    for (int j = 0; j < n; j++) {
+        bool diag = false;
+        for (int q = Ap[j]; q < Ap[j + 1]; q++) {
+            if (Ai[q] > j) return "matrix is not upper triangular";
+            if (Ai[q] == j) diag = true;
+        }
+        if (!diag) return "upper triangle is missing a diagonal entry";
+    }
+    // 1. ordering
+    std::vector<int> perm0;
+    if (user_perm) {
+        perm0.assign(user_perm, user_perm + n);
+        std::vector<char> seen(n, 0);
+        for (int v : perm0) {
+            if (v < 0 || v >= n || seen[v]) return "perm is not a permutation";
+            seen[v] = 1;
+        }
+    } else {
+        minimum_degree(n, Ap, Ai, perm0);
+    }
+    std::vector<int> iperm0(n);
+    for (int k = 0; k < n; k++) iperm0[perm0[k]] = k;
+    // 2. elimination tree of the ordered matrix, postorder it (children ascending), compose
+    std::vector<int> Up, Ui, et0, lnz0;
+    permuted_upper(n, Ap, Ai, iperm0, Up, Ui);
+    etree_counts(n, Up, Ui, et0, lnz0);
+    {
+        std::vector<int> head(n, -1), nextc(n, -1);
+        for (int j = n - 1; j >= 0; j--)
+            if (et0[j] >= 0) { nextc[j] = head[et0[j]]; head[et0[j]] = j; }
+        std::vector<int> post;
+        post.reserve(n);
+        std::vector<int> stack;
+        for (int r = 0; r < n; r++) {
+            if (et0[r] >= 0) continue;
+            stack.push_back(r);
+            while (!stack.empty()) {
+                int v = stack.back();
+                int c = head[v];
+                if (c >= 0) { head[v] = nextc[c]; stack.push_back(c); }
+                else { post.push_back(v); stack.pop_back(); }
+            }
+        }
+        perm.resize(n);
+        for (int k = 0; k < n; k++) perm[k] = perm0[post[k]];
+    }
+    iperm.resize(n);
+    for (int k = 0; k < n; k++) iperm[perm[k]] = k;
+    permuted_upper(n, Ap, Ai, iperm, Up, Ui);
+    nnzL = etree_counts(n, Up, Ui, etree, Lnz);
+    flops = 0;
+    for (int j = 0; j < n; j++) flops += (long long)Lnz[j] * Lnz[j];
+    // 3. column structures of L: struct(j) = lower(A)_j U (struct(children) \ {j})
+    std::vector<int> Lptr(n + 1, 0);
+    for (int j = 0; j < n; j++) Lptr[j + 1] = Lptr[j] + Lnz[j];
+    std::vector<int> Lrows((size_t)Lptr[n]);
+    {
+        // lower entries by column = upper entries by row: transpose Up/Ui
+        std::vector<int> cnt(n + 1, 0);
+        for (int c = 0; c < n; c++)
+            for (int q = Up[c]; q < Up[c + 1]; q++)
+                if (Ui[q] != c) cnt[Ui[q] + 1]++;
+        for (int j = 0; j < n; j++) cnt[j + 1] += cnt[j];
+        std::vector<int> lowr(cnt[n]);
+        std::vector<int> nx(cnt.begin(), cnt.end() - 1);
+        for (int c = 0; c < n; c++)
+            for (int q = Up[c]; q < Up[c + 1]; q++)
+                if (Ui[q] != c) lowr[nx[Ui[q]]++] = c;
+        std::vector<int> mark(n, -1), fill(n, 0);
+        std::vector<std::vector<int>> children(n);
+        for (int j = 0; j < n; j++)
+            if (etree[j] >= 0) children[etree[j]].push_back(j);
+        for (int j = 0; j < n; j++) {
+            int *out = Lrows.data() + Lptr[j];
+            int k = 0;
+            mark[j] = j;
+            for (int q = cnt[j]; q < cnt[j + 1]; q++) {
+                int r = lowr[q];
+                if (mark[r] != j) { mark[r] = j; out[k++] = r; }
+            }
+            for (int c : children[j])
+                for (int q = Lptr[c]; q < Lptr[c + 1]; q++) {
+                    int r = Lrows[q];
+                    if (r != j && mark[r] != j) { mark[r] = j; out[k++] = r; }
+                }
+            if (k != Lnz[j]) return "internal error: column count mismatch";
+            std::sort(out, out + k);
+        }
+    }
+    // 4. fundamental supernodes (consecutive columns, parent = next column, nested structure)
+    const int max_width = 128;
+    sn_start.clear();
+    sn_of.assign(n, 0);
+    for (int j = 0; j < n; j++) {
+        bool merge = j > 0 && etree[j - 1] == j && Lnz[j - 1] == Lnz[j] + 1 && (j - sn_start.back()) < max_width;
+        if (!merge) sn_start.push_back(j);
+        sn_of[j] = (int)sn_start.size() - 1;
+    }
+    ns = (int)sn_start.size();
+    sn_start.push_back(n);
+    rows_ptr.assign(ns + 1, 0);
+    panel_off.assign(ns + 1, 0);
+    max_w = max_nrow = 0;
+    for (int s = 0; s < ns; s++) {
+        int last = sn_start[s + 1] - 1;
+        rows_ptr[s + 1] = rows_ptr[s] + Lnz[last];
+    }
+    rows.resize(rows_ptr[ns]);
+    for (int s = 0; s < ns; s++) {
+        int last = sn_start[s + 1] - 1, w = sn_start[s + 1] - sn_start[s];
+        std::copy(Lrows.begin() + Lptr[last], Lrows.begin() + Lptr[last + 1], rows.begin() + rows_ptr[s]);
+        int nrow = w + Lnz[last];
+        long long sz = (long long)nrow * w;
+        sz = (sz + 1) & ~1LL;  // 16-byte granularity
+        panel_off[s + 1] = panel_off[s] + sz;
+        max_w = std::max(max_w, w);
+        max_nrow = std::max(max_nrow, nrow);
+    }
+    panel_total = panel_off[ns];
+    // 5. pull-based update lists with relative indices
+    std::vector<std::vector<UpdateEntry>> lists(ns);
+    rel.clear();
+    std::vector<long long> work(ns, 0);
+    for (int d = 0; d < ns; d++) {
+        const int *R = rows.data() + rows_ptr[d];
+        int nR = rows_ptr[d + 1] - rows_ptr[d];
+        int wd = sn_start[d + 1] - sn_start[d];
+        int a = 0;
+        while (a < nR) {
+            int t = sn_of[R[a]];
+            int b = a;
+            while (b < nR && sn_of[R[b]] == t) b++;
+            UpdateEntry u{d, a, b, (int)rel.size()};
+            const int *Rt = rows.data() + rows_ptr[t];
+            int nRt = rows_ptr[t + 1] - rows_ptr[t];
+            int wt = sn_start[t + 1] - sn_start[t];
+            for (int i = a; i < nR; i++) {
+                int r = R[i];
+                if (r < sn_start[t + 1]) rel.push_back(r - sn_start[t]);
+                else {
+                    const int *it = std::lower_bound(Rt, Rt + nRt, r);
+                    if (it == Rt + nRt || *it != r) return "internal error: update row missing from target structure";
+                    rel.push_back(wt + (int)(it - Rt));
+                }
+            }
+            lists[t].push_back(u);
+            work[t] += (long long)(nR - a) * (b - a) * wd;
+            a = b;
+        }
+    }
+    upd_ptr.assign(ns + 1, 0);
+    upd.clear();
+    for (int t = 0; t < ns; t++) {
+        std::sort(lists[t].begin(), lists[t].end(), [](const UpdateEntry &x, const UpdateEntry &y) { return x.d < y.d; });
+        for (auto &u : lists[t]) upd.push_back(u);
+        upd_ptr[t + 1] = (int)upd.size();
+    }
+    // 5b. forward-solve row lists (row c of L, grouped by the supernode that stores it)
+    fwd_ptr.assign(n + 1, 0);
+    for (int d = 0; d < ns; d++)
+        for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) fwd_ptr[rows[q] + 1]++;
+    for (int c = 0; c < n; c++) fwd_ptr[c + 1] += fwd_ptr[c];
+    fwd_d.assign(fwd_ptr[n], 0);
+    fwd_row.assign(fwd_ptr[n], 0);
+    {
+        std::vector<int> nx(fwd_ptr.begin(), fwd_ptr.end() - 1);
+        for (int d = 0; d < ns; d++) {
+            int wd = sn_start[d + 1] - sn_start[d];
+            for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) {
+                int c = rows[q];
+                fwd_d[nx[c]] = d;
+                fwd_row[nx[c]] = wd + (q - rows_ptr[d]);
+                nx[c]++;
+            }
+        }
+    }
+    // 6. levels and phases
+    level.assign(ns, 0);
+    nlevels = 0;
+    for (int t = 0; t < ns; t++) {
+        int l = 0;
+        for (int q = upd_ptr[t]; q < upd_ptr[t + 1]; q++) l = std::max(l, level[upd[q].d] + 1);
+        level[t] = l;
+        nlevels = std::max(nlevels, l + 1);
+        int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
+        work[t] += (long long)nrow * w * w / 2 + (long long)nrow * w;
+    }
+    order.resize(ns);
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<char> big(ns);
+    for (int t = 0; t < ns; t++) big[t] = work[t] >= big_task_threshold;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        if (level[x] != level[y]) return level[x] < level[y];
+        if (big[x] != big[y]) return big[x] > big[y];
+        return x < y;
+    });
+    phases.clear();
+    for (int i = 0; i < ns;) {
+        int j = i;
+        while (j < ns && level[order[j]] == level[order[i]] && big[order[j]] == big[order[i]]) j++;
+        int mode = big[order[i]] ? 1 : 0;
+        if (!mode && j - i == 1) mode = 1;  // a lone small task: let the whole CTA help anyway
+        phases.push_back(Phase{mode, i, j});
+        i = j;
+    }
+    // 7. destination of every input entry in the panel storage
+    dest.assign(nnzA, 0);
+    for (int j = 0; j < n; j++)
+        for (int q = Ap[j]; q < Ap[j + 1]; q++) {
+            int a = iperm[Ai[q]], b = iperm[j];
+            int c = std::min(a, b), r = std::max(a, b);
+            int s = sn_of[c];
+            int w = sn_start[s + 1] - sn_start[s];
+            int nrow = w + rows_ptr[s + 1] - rows_ptr[s];
+            int lr;
+            if (r < sn_start[s + 1]) lr = r - sn_start[s];
+            else {
+                const int *Rs = rows.data() + rows_ptr[s];
+                int nRs = rows_ptr[s + 1] - rows_ptr[s];
+                const int *it = std::lower_bound(Rs, Rs + nRs, r);
+                if (it == Rs + nRs || *it != r) return "internal error: entry missing from supernode structure";
+                lr = w + (int)(it - Rs);
+            }
+            dest[q] = panel_off[s] + (long long)(c - sn_start[s]) * nrow + lr;
+        }
+    return "";
+}
+
+}  // namespace cb200

@@ -79,14 +79,15 @@ def _csc(a: sp.spmatrix):
 
 
 def lqc(T: int, n_x: int, n_u: int, n_soc: int, seed: int, *, h: float = 0.05, u_max: float = 10.0,
-        mu: float = 0.5, c0: float = 5.0, q_scale: float = 0.3) -> ConicProblem:
+        mu: float = 0.5, c0: float = 10.0, q_scale: float = 0.3) -> ConicProblem:
     """Build one ``LQC(T, n_x, n_u, n_soc, seed)`` instance; PCG64(seed).
 
     Two constants differ from SURVEY.md section 8(d) (c0 = 1, q ~ N(0,1)): with those the *reference algorithm
     itself* (as restated by the oracle, including its UMFPACK-style fallback) aborts with "cone search failure" on
     cfg3 after 53 iterations, because the SOC(3) reduced blocks are far from symmetric off the central path
-    (SURVEY.md section 3.3 quirk).  With c0 = 5 and q ~ 0.3 N(0,1) the reference converges on cfg2 (14 iterations)
-    and cfg3 (16 iterations) while still needing ~7 refinement passes per Newton step.  See DESIGN.md.
+    (SURVEY.md section 3.3 quirk); with c0 = 5 one cfg3 seed in 16 still fails to converge in 600 iterations.  With
+    c0 = 10 and q ~ 0.3 N(0,1) the reference converges on every seed tried (cfg3 seeds 0..15: 7-10 Newton iterations,
+    at most one fallback solve) while still needing several refinement passes per Newton step.  See DESIGN.md.
     """
     assert n_u % 3 == 0 or n_soc == 0
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -101,52 +102,54 @@ def lqc(T: int, n_x: int, n_u: int, n_soc: int, seed: int, *, h: float = 0.05, u
     B = h * rng.standard_normal((n_x, n_u))
     xhat = rng.standard_normal(n_x)
     m = T * n_x
-    G = sp.lil_matrix((m, n))
+    ts = np.arange(T - 1)
+    rows, cols, vals = [], [], []
+
+    def dense_blocks(block, row0, col0):
+        """COO triplets of `block` placed at (row0[k], col0[k]) for every k."""
+        nr, nc = block.shape
+        ii, jj = np.meshgrid(np.arange(nr), np.arange(nc), indexing="ij")
+        rows.append((row0[:, None, None] + ii[None]).ravel())
+        cols.append((col0[:, None, None] + jj[None]).ravel())
+        vals.append(np.broadcast_to(block, (len(row0), nr, nc)).ravel())
+
+    dense_blocks(-A, ts * n_x, ts * nz)
+    dense_blocks(-B, ts * n_x, ts * nz + n_x)
+    eye_r = (ts[:, None] * n_x + np.arange(n_x)[None]).ravel()
+    rows.append(eye_r); cols.append(((ts[:, None] + 1) * nz + np.arange(n_x)[None]).ravel()); vals.append(np.ones(len(eye_r)))
+    rows.append((T - 1) * n_x + np.arange(n_x)); cols.append(np.arange(n_x)); vals.append(np.ones(n_x))
+    G = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(m, n))
     g0 = np.zeros(m)
-    for t in range(T - 1):
-        r = t * n_x
-        G[r:r + n_x, xs(t + 1):xs(t + 1) + n_x] = np.eye(n_x)
-        G[r:r + n_x, xs(t):xs(t) + n_x] = -A
-        G[r:r + n_x, us(t):us(t) + n_u] = -B
-    r = (T - 1) * n_x
-    G[r:r + n_x, xs(0):xs(0) + n_x] = np.eye(n_x)
-    g0[r:r + n_x] = -xhat
+    g0[(T - 1) * n_x:] = -xhat
 
     # --- stage costs
-    Q = sp.lil_matrix((n, n))
     q = np.zeros(n)
+    rows, cols, vals = [], [], []
     for t in range(T):
         d = nz if t < T - 1 else n_x
         M = rng.standard_normal((d, d))
         Wt = M.T @ M / nz + 0.1 * np.eye(d)
-        Q[xs(t):xs(t) + d, xs(t):xs(t) + d] = Wt
+        ii, jj = np.meshgrid(np.arange(d), np.arange(d), indexing="ij")
+        rows.append((xs(t) + ii).ravel()); cols.append((xs(t) + jj).ravel()); vals.append(Wt.ravel())
         q[xs(t):xs(t) + d] = q_scale * rng.standard_normal(d)
+    Q = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
 
     # --- cones: box rows first (nonnegative), then SOC(3) blocks ordered by (stage, triple)
     n_box = 2 * n_u * (T - 1)
-    socs = []
-    for k in range(n_soc):
-        t = k % (T - 1)
-        j = (k // (T - 1)) % (n_u // 3)
-        socs.append((t, j))
-    socs.sort()
+    socs = sorted((k % (T - 1), (k // (T - 1)) % max(n_u // 3, 1)) for k in range(n_soc))
     p = n_box + 3 * n_soc
-    C = sp.lil_matrix((p, n))
+    rows, cols, vals = [], [], []
     h0 = np.zeros(p)
-    for t in range(T - 1):
-        r = 2 * n_u * t
-        for i in range(n_u):
-            C[r + i, us(t) + i] = 1.0           # u - u_min >= 0
-            h0[r + i] = u_max
-            C[r + n_u + i, us(t) + i] = -1.0    # u_max - u >= 0
-            h0[r + n_u + i] = u_max
+    ucol = (ts[:, None] * nz + n_x + np.arange(n_u)[None]).ravel()
+    r_lo = (2 * n_u * ts[:, None] + np.arange(n_u)[None]).ravel()
+    rows += [r_lo, r_lo + n_u]; cols += [ucol, ucol]; vals += [np.ones(len(ucol)), -np.ones(len(ucol))]
+    h0[:n_box] = u_max
     for k, (t, j) in enumerate(socs):
         r = n_box + 3 * k
-        a, b, c = us(t) + 3 * j, us(t) + 3 * j + 1, us(t) + 3 * j + 2
-        C[r, a] = mu
+        a = us(t) + 3 * j
+        rows.append(np.array([r, r + 1, r + 2])); cols.append(np.array([a, a + 1, a + 2])); vals.append(np.array([mu, 1.0, 1.0]))
         h0[r] = c0
-        C[r + 1, b] = 1.0
-        C[r + 2, c] = 1.0
+    C = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(p, n))
 
     # --- initial guess: states interpolate xhat -> 0, tiny actions
     x0 = np.zeros(n)
@@ -169,6 +172,11 @@ def lqc(T: int, n_x: int, n_u: int, n_soc: int, seed: int, *, h: float = 0.05, u
 # BASELINE.json configs 2-4 (cfg2 N=2142, cfg3 N=4584, cfg4 = 64 seeds of cfg3)
 def cfg2(instance: int = 0) -> ConicProblem:
     return lqc(50, 12, 6, 20, 1000 * 2 + instance)
+
+
+def cfg2_hard(instance: int = 0) -> ConicProblem:
+    """cfg2 with more active cones (c0 = 5): refinement fails on a few iterations, exercising the fallback solve."""
+    return lqc(50, 12, 6, 20, 1000 * 2 + instance, c0=5.0)
 
 
 def cfg3(instance: int = 0) -> ConicProblem:

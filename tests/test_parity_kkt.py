@@ -142,7 +142,7 @@ def test_inertia_correction_schedule_matches_oracle(backend):
 
 
 @pytest.mark.parametrize("backend", backends.BACKENDS)
-@pytest.mark.parametrize("make", [lqc.tiny, lqc.cfg2])
+@pytest.mark.parametrize("make", [lqc.tiny, lqc.cfg2, lqc.cfg2_hard])
 def test_lq_solve_on_device_matches_oracle(backend, make):
     """Whole solve! on the device (LQ callbacks) vs the oracle's solve!: same iteration counts, same solution."""
     P = make()
@@ -161,6 +161,8 @@ def test_lq_solve_on_device_matches_oracle(backend, make):
     assert st["total_iterations"] == o.stats["total_iterations"]
     assert st["outer"] == o.stats["outer"]
     assert st["fallbacks"] == o.stats["lu_fallbacks"]
+    if make is lqc.cfg2_hard:
+        assert st["fallbacks"] > 0          # the GMRES stand-in for `J \\ R` (search_direction.jl:22) was exercised
     w = k.get("POINT")[0]
     assert rel(w, o.solution) < 1e-6
     sc = k.scalars()

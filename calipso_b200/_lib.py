@@ -38,6 +38,11 @@ I_COUNT = 24
 STATUS_TEXT = {0: "ok", 1: "inertia correction failure", 2: "iterative refinement failure", 3: "cone search failure",
                4: "zero pivot"}
 
+PROFILE = ["assemble", "factor_leaves", "factor_small", "factor_big_stage", "factor_big_gemm", "factor_big_panel",
+           "factor_big_generic", "solve_fwd", "solve_bwd", "rhs_recover", "jtimes", "eval_linesearch", "cone_residual",
+           "inertia", "total"]
+PROF_COUNT = 16
+
 EV_OBJECTIVE, EV_GRADIENT, EV_EQUALITY, EV_CONE, EV_EQUALITY_DUAL_GRAD, EV_CONE_DUAL_GRAD = 1, 2, 4, 8, 16, 32
 EV_HESSIAN, EV_EQUALITY_JAC, EV_CONE_JAC = 64, 128, 256
 CONE_BARRIER, CONE_BARRIER_GRADIENT, CONE_PRODUCT = 1, 2, 4
@@ -77,6 +82,7 @@ SYMBOLS = {
     "cb200_get_array": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
     "cb200_get_stats": (C.c_int, [vp, c_ip, C.c_int, C.c_int]),
     "cb200_array_length": (C.c_int, [vp, C.c_int]),
+    "cb200_get_profile": (C.c_int, [vp, c_llp, C.c_int]),
     "cb200_device_ptr": (vp, [vp, C.c_int]),
     "cb200_stream": (vp, [vp]),
     "cb200_synchronize": (C.c_int, [vp]),

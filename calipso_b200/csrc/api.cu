@@ -24,9 +24,11 @@ struct Batch {
     long long ksize;
     double *w, *cand, *step, *res, *err, *corr, *tmp;
     double *grad, *gyx, *hzx, *g, *h, *Wv, *Gv, *Cv, *prod, *bgrad, *lambda;
-    double *panels, *D, *Dinv, *xs, *rs, *xp, *mgrad, *q, *g0, *h0, *filter, *krylov, *scal;
+    double *panels, *D, *Dinv, *Tinv, *Lcsr, *xs, *rs, *xp, *mgrad, *q, *g0, *h0, *filter, *krylov, *scal;
     double *Aval, *rhs;
     int *istat;
+    long long *prof;
+    int scratch_doubles;
     __device__ __forceinline__ Inst inst(const DevProblem &P, int b) const
     {
         Inst I;
@@ -38,6 +40,9 @@ struct Batch {
         I.Wv = Wv + b * (long long)P.nnzW; I.Gv = Gv + b * (long long)P.nnzG; I.Cv = Cv + b * (long long)P.nnzC;
         I.prod = prod + b * p; I.bgrad = bgrad + b * p; I.lambda = lambda + b * m;
         I.panels = panels + b * P.panel_total; I.D = D + b * N; I.Dinv = Dinv + b * N;
+        I.Tinv = Tinv + b * P.tinv_total;
+        I.Lcsr = Lcsr + b * P.lcsr_total;
+        I.prof = prof ? prof + b * (long long)PROF_COUNT : nullptr;
         I.xs = xs + b * N; I.rs = rs + b * N; I.xp = xp + b * N; I.mgrad = mgrad + b * N;
         I.q = q + b * n; I.g0 = g0 + b * m; I.h0 = h0 + b * p;
         I.filter = filter + b * 4LL * F;
@@ -49,9 +54,21 @@ struct Batch {
 };
 
 #define CB_THREADS 256
+extern __shared__ __align__(16) double cb_dyn_smem[];
+#define CTX_SETUP                                                                                          \
+    __shared__ double red[34];                                                                             \
+    __shared__ __align__(8) unsigned long long cb_bars[2];                                                 \
+    __shared__ unsigned cb_bar_uses;                                                                       \
+    if (threadIdx.x == 0) {                                                                                \
+        mbar_init(&cb_bars[0], 1);                                                                         \
+        mbar_init(&cb_bars[1], 1);                                                                         \
+        cb_bar_uses = 0;                                                                                   \
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                               \
+    }                                                                                                      \
+    __syncthreads();                                                                                       \
+    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red, B.scratch_doubles > 0 ? cb_dyn_smem : nullptr, cb_bars, &cb_bar_uses};
 #define KERNEL_PROLOGUE                                   \
-    __shared__ double red[34];                            \
-    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red};   \
+    CTX_SETUP                                             \
     const int b = blockIdx.x;                             \
     if (b >= B.count) return;                             \
     Inst I = B.inst(P, b);
@@ -133,26 +150,25 @@ __global__ void __launch_bounds__(CB_THREADS) k_lq_step(DevProblem P, Batch B, O
 // roofline bench.py reports (B_unit).
 __global__ void __launch_bounds__(CB_THREADS) k_ldl_factor(DevProblem P, Batch B, int assemble_generic)
 {
-    __shared__ double red[34];
-    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red};
+    CTX_SETUP
     const int b = blockIdx.x;
     if (b >= B.count) return;
     double *pan = B.panels + b * P.panel_total;
     double *D = B.D + b * (long long)P.N, *Dinv = B.Dinv + b * (long long)P.N;
     int *istat = B.istat + b * (long long)I_COUNT;
     if (assemble_generic) matrix_assemble(ctx, P, pan, B.Aval + b * (long long)P.nnzA);
-    ldl_factor(ctx, P, pan, D, Dinv, istat);
+    ldl_factor(ctx, P, pan, D, Dinv, B.Tinv + b * P.tinv_total, B.Lcsr + b * P.lcsr_total, istat, B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
 __global__ void __launch_bounds__(CB_THREADS) k_ldl_solve(DevProblem P, Batch B)
 {
-    __shared__ double red[34];
-    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, red};
+    CTX_SETUP
     const int b = blockIdx.x;
     if (b >= B.count) return;
     double *rhs = B.rhs + b * (long long)P.N;
-    ldl_solve(ctx, P, B.panels + b * P.panel_total, B.Dinv + b * (long long)P.N, rhs, rhs, B.xp + b * (long long)P.N,
-              B.istat + b * (long long)I_COUNT);
+    ldl_solve(ctx, P, B.panels + b * P.panel_total, B.D + b * (long long)P.N, B.Dinv + b * (long long)P.N,
+              B.Tinv + b * P.tinv_total, B.Lcsr + b * P.lcsr_total, rhs, rhs, B.xp + b * (long long)P.N, B.istat + b * (long long)I_COUNT,
+              B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
 // KKT path: assemble + factor with the current regularisation (no inertia loop) -- used by the roofline bench
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_kkt_factor_solve(DevProblem P, B
 {
     KERNEL_PROLOGUE
     kkt_assemble(ctx, P, I);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.istat);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, I.prof);
     for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
 }
 
@@ -208,6 +224,7 @@ struct cb200_handle {
     std::vector<void *> allocs;
     ArrayDesc arr[CB200_NUM_ARRAYS]{};
     long long *d_counts = nullptr, *h_counts = nullptr;
+    size_t smem_bytes = 0;
     void *comm = nullptr;
     int nranks = 1;
     int nnzW = 0, nnzG = 0, nnzC = 0;
@@ -274,7 +291,19 @@ static int common_init(cb200_handle *h, int device)
     return 0;
 }
 
-static const int BIG_TASK_THRESHOLD = 3000;   // multiply-adds above which a supernode gets the whole CTA
+static const int BIG_TASK_THRESHOLD = 3000;
+
+static bool finish_batch(cb200_handle *h)
+{   // profile counters + dynamic shared memory of the factor/solve kernels
+    void *d = nullptr;
+    size_t bytes = (size_t)h->batch * PROF_COUNT * sizeof(long long);
+    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemset(d, 0, bytes) != cudaSuccess) return false;
+    h->allocs.push_back(d);
+    h->B.prof = (long long *)d;
+    h->B.scratch_doubles = h->sym().scratch_doubles;
+    h->smem_bytes = (size_t)h->B.scratch_doubles * sizeof(double);
+    return true;
+}   // multiply-adds above which a supernode gets the whole CTA
 
 extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, int nsoc, const int *soc_dims,
                                       const int *Wp, const int *Wi, const int *Gp, const int *Gi, const int *Cp,
@@ -309,6 +338,7 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
     B.Wv = dalloc(h, nnzW, ok); B.Gv = dalloc(h, nnzG, ok); B.Cv = dalloc(h, nnzC, ok);
     B.prod = dalloc(h, p, ok); B.bgrad = dalloc(h, p, ok); B.lambda = dalloc(h, m, ok);
     B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
+    B.Tinv = dalloc(h, P.tinv_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
     B.xs = dalloc(h, N, ok); B.rs = dalloc(h, N, ok); B.xp = dalloc(h, N, ok); B.mgrad = dalloc(h, N, ok);
     B.q = dalloc(h, n, ok); B.g0 = dalloc(h, m, ok); B.h0 = dalloc(h, p, ok);
     B.filter = dalloc(h, 4LL * B.F, ok);
@@ -322,6 +352,7 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
         h->allocs.push_back(d);
         B.istat = (int *)d;
     }
+    ok = ok && finish_batch(h);
     if (!ok) { fail(std::string("device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError())); cb200_destroy(h); return nullptr; }
     ArrayDesc *a = h->arr;
     a[CB200_POINT] = {B.w, T}; a[CB200_CANDIDATE] = {B.cand, T}; a[CB200_STEP] = {B.step, T};
@@ -360,6 +391,7 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     Batch &B = h->B;
     B.count = batch;
     B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
+    B.Tinv = dalloc(h, P.tinv_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
     B.xp = dalloc(h, N, ok); B.Aval = dalloc(h, P.nnzA, ok); B.rhs = dalloc(h, N, ok);
     {
         void *d = nullptr;
@@ -368,6 +400,7 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
         h->allocs.push_back(d);
         B.istat = (int *)d;
     }
+    ok = ok && finish_batch(h);
     if (!ok) { fail("device allocation/upload failed"); cb200_destroy(h); return nullptr; }
     h->arr[CB200_PIVOTS] = {B.D, N};
     h->arr[CB200_MATRIX_VALUES] = {B.Aval, P.nnzA};
@@ -417,18 +450,7 @@ extern "C" int cb200_get_factor(cb200_handle *h, int instance, int *Lp, int *Li,
     std::vector<double> pan((size_t)S.panel_total);
     CUDA_OK(cudaMemcpy(pan.data(), h->B.panels + (long long)instance * S.panel_total, sizeof(double) * pan.size(), cudaMemcpyDeviceToHost));
     CUDA_OK(cudaMemcpy(D, h->B.D + (long long)instance * S.N, sizeof(double) * S.N, cudaMemcpyDeviceToHost));
-    Lp[0] = 0;
-    for (int s = 0; s < S.ns; s++) {
-        int c0 = S.sn_start[s], c1 = S.sn_start[s + 1], w = c1 - c0;
-        int nR = S.rows_ptr[s + 1] - S.rows_ptr[s], nrow = w + nR;
-        const double *Ps = pan.data() + S.panel_off[s];
-        for (int c = c0; c < c1; c++) {
-            int k = Lp[c];
-            for (int r = c + 1; r < c1; r++) { Li[k] = r; Lx[k] = Ps[(r - c0) + (long long)(c - c0) * nrow]; k++; }
-            for (int i = 0; i < nR; i++) { Li[k] = S.rows[S.rows_ptr[s] + i]; Lx[k] = Ps[(w + i) + (long long)(c - c0) * nrow]; k++; }
-            Lp[c + 1] = k;
-        }
-    }
+    extract_factor(S, pan.data(), Lp, Li, Lx);
     return 0;
 }
 
@@ -467,6 +489,16 @@ extern "C" int cb200_get_stats(cb200_handle *h, int *host, int first, int count)
     return 0;
 }
 
+extern "C" int cb200_get_profile(cb200_handle *h, long long *host, int reset)
+{   // [batch][16] cycle counters (see PROF_* in device_core.h)
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    size_t bytes = (size_t)h->batch * PROF_COUNT * sizeof(long long);
+    if (host) CUDA_OK(cudaMemcpy(host, h->B.prof, bytes, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_OK(cudaMemset(h->B.prof, 0, bytes));
+    return 0;
+}
+
 extern "C" int cb200_array_length(const cb200_handle *h, int which)
 {
     if (which < 0 || which >= CB200_NUM_ARRAYS || !h->arr[which].ptr) return -1;
@@ -498,11 +530,23 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
         kernel<<<h->batch, CB_THREADS, 0, h->stream>>>(__VA_ARGS__);          \
         CUDA_OK(cudaGetLastError());                                          \
     } while (0)
+// kernels that factor or solve get the CTA work area (panel + Y staging) as dynamic shared memory
+#define LAUNCH_SMEM(kernel, ...)                                                                          \
+    do {                                                                                                  \
+        CUDA_OK(cudaSetDevice(h->device));                                                                \
+        static size_t configured_##kernel = 0;                                                            \
+        if (h->smem_bytes > configured_##kernel) {                                                        \
+            CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
+            configured_##kernel = h->smem_bytes;                                                          \
+        }                                                                                                 \
+        kernel<<<h->batch, CB_THREADS, h->smem_bytes, h->stream>>>(__VA_ARGS__);                          \
+        CUDA_OK(cudaGetLastError());                                                                      \
+    } while (0)
 #define NEED_KKT() if (h->generic) return fail("not available on a LinearSolver-seam handle")
 
 extern "C" int cb200_cone(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); LAUNCH(k_cone, h->P, h->B, flags, at_candidate); return 0; }
 extern "C" int cb200_residual(cb200_handle *h) { NEED_KKT(); LAUNCH(k_residual, h->P, h->B); return 0; }
-extern "C" int cb200_search_direction(cb200_handle *h) { NEED_KKT(); LAUNCH(k_search_direction, h->P, h->B, h->opt); return 0; }
+extern "C" int cb200_search_direction(cb200_handle *h) { NEED_KKT(); LAUNCH_SMEM(k_search_direction, h->P, h->B, h->opt); return 0; }
 extern "C" int cb200_cone_search(cb200_handle *h) { NEED_KKT(); LAUNCH(k_cone_search, h->P, h->B, h->opt); return 0; }
 extern "C" int cb200_apply_step(cb200_handle *h) { NEED_KKT(); LAUNCH(k_apply_step, h->P, h->B); return 0; }
 extern "C" int cb200_lq_evaluate(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); LAUNCH(k_lq_evaluate, h->P, h->B, flags, at_candidate); return 0; }
@@ -510,10 +554,10 @@ extern "C" int cb200_lq_begin(cb200_handle *h, int warmstart) { NEED_KKT(); LAUN
 extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
 {
     NEED_KKT();
-    for (int k = 0; k < iterations; k++) LAUNCH(k_lq_step, h->P, h->B, h->opt);
+    for (int k = 0; k < iterations; k++) LAUNCH_SMEM(k_lq_step, h->P, h->B, h->opt);
     return 0;
 }
-extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); LAUNCH(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
+extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); LAUNCH_SMEM(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
 
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host)
 {
@@ -564,13 +608,13 @@ extern "C" int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, l
 extern "C" int cb200_ldl_factorize(cb200_handle *h)
 {
     if (!h->generic) return fail("cb200_ldl_factorize needs a handle from cb200_ldl_create");
-    LAUNCH(k_ldl_factor, h->P, h->B, 1);
+    LAUNCH_SMEM(k_ldl_factor, h->P, h->B, 1);
     return 0;
 }
 extern "C" int cb200_ldl_solve(cb200_handle *h)
 {
     if (!h->generic) return fail("cb200_ldl_solve needs a handle from cb200_ldl_create");
-    LAUNCH(k_ldl_solve, h->P, h->B);
+    LAUNCH_SMEM(k_ldl_solve, h->P, h->B);
     return 0;
 }
 extern "C" int cb200_ldl_inertia(cb200_handle *h, int *out)

@@ -62,7 +62,17 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const int *rel;
     const int *order;
     const Phase *phases;
-    const int *fwd_ptr, *fwd_d, *fwd_row;      // per permuted column: (descendant supernode, local row) pairs
+    const int *fwd_ptr;                        // per permuted column: range of (descendant, row) pairs in fwd
+    const FwdEntry *fwd;                       // (non-leaf descendants)
+    const int *lcsr_ptr, *lcsr_col, *leaf_csr_pos;   // row-ordered copy of the singleton-leaf columns
+    long long lcsr_total;
+    const int *big_index;                      // [ns] -> big[] (shared-memory path) or -1
+    const BigTarget *big;
+    const YChunk *ychunks;
+    const int *ystage_src, *ystage_dst, *ypiv;
+    long long tinv_total;
+    const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
+    int nbig, max_sb_doubles, solve_smem;
     // assembly destinations (offsets into the panel storage)
     const long long *dW, *dG, *dC, *dY, *dZnn, *dZsoc;
     const long long *dA;                       // generic-matrix mode (LinearSolver seam): one per input entry
@@ -84,6 +94,13 @@ struct Options {      // src/solver/options.jl:6-59, hot-path subset (same defau
         machine_tolerance;
     int max_filter;
     int gmres_restart, gmres_max_cycles;   // fallback when refinement fails (replaces the reference's UMFPACK J\R)
+};
+
+// cycle counters (thread 0 of each CTA, clock64) -- where a Newton iteration spends its time
+enum {
+    PROF_ASSEMBLE = 0, PROF_FACTOR_LEAVES, PROF_FACTOR_SMALL, PROF_FACTOR_BIG_STAGE, PROF_FACTOR_BIG_GEMM,
+    PROF_FACTOR_BIG_PANEL, PROF_FACTOR_BIG_GENERIC, PROF_SOLVE_FWD, PROF_SOLVE_BWD, PROF_RHS_RECOVER, PROF_JTIMES,
+    PROF_EVAL_LINESEARCH, PROF_CONE_RESIDUAL, PROF_INERTIA, PROF_TOTAL, PROF_COUNT = 16
 };
 
 // per-instance scalar slots
@@ -108,7 +125,8 @@ struct Inst {         // device pointers of ONE instance
     double *Wv, *Gv, *Cv;                              // values at the patterns
     double *prod, *bgrad;                              // [p]
     double *lambda;                                    // [m]
-    double *panels, *D, *Dinv;                         // factor
+    double *panels, *D, *Dinv, *Tinv, *Lcsr;           // factor (+ M blocks of the big supernodes, leaf CSR copy)
+    long long *prof;                                   // [PROF_COUNT] cycle counters (may be null)
     double *xs, *rs, *xp;                              // [N] reduced solution / rhs / permuted scratch
     double *mgrad;                                     // [N]
     double *q, *g0, *h0;                               // LQ data (may be null)
@@ -123,6 +141,9 @@ struct Ctx {
     int tid, nthr;     // thread index / count inside the cooperating scope
     int warp_scope;    // 1: the scope is a single warp
     double *red;       // CTA scratch for reductions (>= 34 doubles), unused in warp scope
+    double *scratch;   // shared-memory work area of the CTA (P.scratch_doubles doubles); heap in host emulation
+    unsigned long long *bars;   // two mbarriers in static shared memory, initialised once per kernel (device only)
+    unsigned *bar_uses;         // number of TMA copies issued so far in this kernel (selects slot and phase parity)
     CB_DEV void sync() const
     {
 #if CB_ON_DEVICE
@@ -410,10 +431,53 @@ CB_DEVN void matrix_assemble(const Ctx &ctx, const DevProblem &P, double *pan, c
     ctx.sync();
 }
 
+// ------------------------------------------------------------------------------------------------ profiling
+struct ProfTimer {       // thread 0 of the CTA accumulates clock64() deltas into per-instance slots
+    long long *slots;
+    long long t0;
+    CB_DEV void start()
+    {
+#if CB_ON_DEVICE
+        if (slots && threadIdx.x == 0) t0 = clock64();
+#endif
+    }
+    CB_DEV void stop(int slot)
+    {
+#if CB_ON_DEVICE
+        if (slots && threadIdx.x == 0) { long long t1 = clock64(); slots[slot] += t1 - t0; t0 = t1; }
+#endif
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ supernodal LDL^T
-// One supernode: pull the updates of its descendants, then factor the (nrow x w) panel in place.  Scope = the
-// threads in ctx (a warp or the CTA).  Unscaled columns are kept until the end so that each pivot step needs one
-// barrier; the final pass divides by the pivots (L = A D^-1) and publishes D, 1/D.
+// In-place LDL' of a column-major block: `rows` x `w`, leading dimension ld, pivots on the diagonal of the top w x w
+// part.  Unscaled columns are kept until the end so that each pivot step needs one barrier; the final pass divides by
+// the pivots (L = A D^-1).  Works on shared or global memory.
+CB_DEV void panel_factor(const Ctx &ctx, double *Ps, int rows, int w, int ld)
+{
+    for (int k = 0; k < w; k++) {
+        ctx.sync();
+        const double dk = Ps[k + (long long)k * ld];
+        const double dinv = dk != 0.0 ? 1.0 / dk : 0.0;
+        const int ncol = w - 1 - k;
+        PAR_FOR(e, ncol * rows) {
+            int j = k + 1 + e / rows, i = e % rows;
+            if (i >= j) Ps[i + (long long)j * ld] -= Ps[i + (long long)k * ld] * (Ps[j + (long long)k * ld] * dinv);
+        }
+    }
+    ctx.sync();
+    PAR_FOR(e, w * rows) {
+        int k = e / rows, i = e % rows;
+        if (i > k) {
+            double dk = Ps[k + (long long)k * ld];
+            Ps[i + (long long)k * ld] *= (dk != 0.0 ? 1.0 / dk : 0.0);
+        }
+    }
+    ctx.sync();
+}
+
+// Generic supernode (any scope, panel in global memory): pull the updates of the descendants one by one, then
+// factor the (nrow x w) panel in place.
 CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, int s)
 {
     const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
@@ -437,30 +501,267 @@ CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, d
         }
         ctx.sync();
     }
-    for (int k = 0; k < w; k++) {
-        ctx.sync();
-        const double dk = Ps[k + (long long)k * nrow];
-        const double dinv = dk != 0.0 ? 1.0 / dk : 0.0;
-        const int ncol = w - 1 - k;
-        PAR_FOR(e, ncol * nrow) {
-            int j = k + 1 + e / nrow, i = e % nrow;
-            if (i >= j) Ps[i + (long long)j * nrow] -= Ps[i + (long long)k * nrow] * (Ps[j + (long long)k * nrow] * dinv);
-        }
-    }
-    ctx.sync();
-    PAR_FOR(e, w * nrow) {
-        int k = e / nrow, i = e % nrow;
-        if (i > k) {
-            double dk = Ps[k + (long long)k * nrow];
-            Ps[i + (long long)k * nrow] *= (dk != 0.0 ? 1.0 / dk : 0.0);
-        }
-    }
+    panel_factor(ctx, Ps, nrow, w, nrow);
     PAR_FOR(k, w) {
         double dk = Ps[k + (long long)k * nrow];
         D[c0 + k] = dk;
         Dinv[c0 + k] = dk != 0.0 ? 1.0 / dk : 0.0;
     }
     ctx.sync();
+}
+
+#if CB_ON_DEVICE
+// Blocked LDL' of a (rows x w) column-major panel in shared memory, CUDA-specific: NB columns at a time, one thread
+// per row keeps its NB entries in registers; the pivot row is broadcast through shared memory (double-buffered, one
+// barrier per pivot); the trailing columns get a rank-NB update with 4x4 register tiles.  Same arithmetic as
+// panel_factor (right-looking, L = A D^-1).  dd[] receives the pivots.
+template <int NB>
+__device__ __forceinline__ void panel_factor_smem(double *S, int rows, int w, int ld, double *pivbuf, double *dd)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int kb = 0; kb < w; kb += NB) {
+        const int nb = min(NB, w - kb);
+        double a[NB];
+        for (int rbase = kb; rbase < rows; rbase += nthr) {     // normally one pass (rows <= blockDim)
+            const int i = rbase + tid;
+            const bool active = i < rows;
+#pragma unroll
+            for (int cc = 0; cc < NB; cc++) a[cc] = (active && cc < nb) ? S[i + (kb + cc) * ld] : 0.0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+                if (k < nb) {
+                    // broadcast column k of the diagonal block (unscaled): pb[c] = A[kb+c, kb+k], c >= k; pb[k] = pivot
+                    double *pb = pivbuf + (k & 1) * NB;
+                    if (rbase == kb && i >= kb + k && i < kb + nb) pb[i - kb] = a[k];
+                    __syncthreads();
+                    const double d = pb[k];
+                    const double dinv = d != 0.0 ? 1.0 / d : 0.0;
+                    if (active && i > kb + k) {
+                        const double lik = a[k] * dinv;
+#pragma unroll
+                        for (int cc = 0; cc < NB; cc++)
+                            if (cc > k) a[cc] -= lik * pb[cc];
+                        a[k] = lik;
+                    }
+                    if (rbase == kb && i == kb + k) dd[kb + k] = d;
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int cc = 0; cc < NB; cc++)
+                    if (cc < nb) S[i + (kb + cc) * ld] = a[cc];
+            }
+            __syncthreads();
+        }
+        // trailing update: S[i, j] -= sum_c L[i, kb+c] d_c L[j, kb+c] for j >= kb+nb, i >= j
+        const int j0 = kb + nb;
+        if (j0 < w) {
+            const int ntJ = (w - j0 + 3) >> 2, ntI = (rows - j0 + 3) >> 2;
+            for (int tile = tid; tile < ntI * ntJ; tile += nthr) {
+                const int ti = tile % ntI, tj = tile / ntI;
+                if (ti >= tj) {
+                    const int ib = j0 + 4 * ti, jb = j0 + 4 * tj;
+                    double acc[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < NB; cc++) {
+                        if (cc < nb) {
+                            const double dc = dd[kb + cc];
+                            double av[4], bv[4];
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                av[r] = (ib + r < rows) ? S[ib + r + (kb + cc) * ld] : 0.0;
+                                bv[r] = (jb + r < rows) ? S[jb + r + (kb + cc) * ld] * dc : 0.0;
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+#pragma unroll
+                                for (int q = 0; q < 4; q++) acc[r][q] += av[r] * bv[q];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const int Ii = ib + r, Jj = jb + q;
+                            if (Ii < rows && Jj < w && Ii >= Jj) S[Ii + Jj * ld] -= acc[r][q];
+                        }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+#endif
+
+// CTA-scope supernode on the shared-memory path.  All descendant columns that touch the target are staged as the
+// columns of a dense matrix Y (rows = target rows) and applied as ONE register-tiled GEMM  S -= Y diag(D) Y_top'
+// instead of one barrier per descendant.  The panel carries w extra rows initialised to the identity: after the
+// elimination they hold M = L_tt^-T D_t^-1, which turns the triangular solves of this supernode into mat-vecs
+// (ldl_solve).  Layout of ctx.scratch: S[(nrow+w) x w] | Y[ldy x kc] | Dy[kc].
+CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv,
+                                 double *Tinv, int s, const BigTarget bt, ProfTimer &pt)
+{
+    const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+    const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
+    const int ldp = nrow + w, ldy = bt.ldy;
+    double *Ps = pan + P.panel_off[s];
+    double *S = ctx.scratch;
+    double *Y = S + (((long long)ldp * w + 1) & ~1LL);
+    pt.start();
+#if CB_ON_DEVICE
+    {   // panel + identity rows, column by column (coalesced, no div/mod)
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int k = wid; k < w; k += nw) {
+            const double *src = Ps + k * nrow;
+            double *dst = S + k * ldp;
+            for (int i = lane; i < nrow; i += 32) dst[i] = src[i];
+            for (int i = lane; i < w; i += 32) dst[nrow + i] = (i == k) ? 1.0 : 0.0;
+        }
+    }
+#else
+    PAR_FOR(e, ldp * w) {
+        int k = e / ldp, i = e % ldp;
+        S[e] = i < nrow ? Ps[i + (long long)k * nrow] : (i - nrow == k ? 1.0 : 0.0);
+    }
+#endif
+    for (int ci = bt.chunk_begin; ci < bt.chunk_end; ci++) {
+        const YChunk ch = P.ychunks[ci];
+        const int kc = ch.col_end - ch.col_begin;
+        double *Dy = Y + (long long)ldy * kc;
+#if CB_ON_DEVICE
+        {
+            double2 *Y2 = reinterpret_cast<double2 *>(Y);
+            const int n2 = (ldy * kc) >> 1;     // ldy is a multiple of 4
+            for (int e = ctx.tid; e < n2; e += ctx.nthr) Y2[e] = make_double2(0.0, 0.0);
+        }
+#else
+        PAR_FOR(e, ldy * kc) Y[e] = 0.0;
+#endif
+        PAR_FOR(cc, kc) Dy[cc] = D[P.ypiv[ch.piv_begin + cc]];
+        ctx.sync();
+#if CB_ON_DEVICE
+        {   // scatter with four loads in flight per thread
+            const int nst = ch.stage_end - ch.stage_begin;
+            const int *src = P.ystage_src + ch.stage_begin, *dst = P.ystage_dst + ch.stage_begin;
+            for (int e = ctx.tid; e < nst; e += 4 * ctx.nthr) {
+                int sidx[4], didx[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int ee = e + u * ctx.nthr;
+                    sidx[u] = ee < nst ? src[ee] : -1;
+                    didx[u] = ee < nst ? dst[ee] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = sidx[u] >= 0 ? pan[sidx[u]] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (sidx[u] >= 0) Y[didx[u]] = v[u];
+            }
+        }
+#else
+        PAR_FOR(e, ch.stage_end - ch.stage_begin) Y[P.ystage_dst[ch.stage_begin + e]] = pan[P.ystage_src[ch.stage_begin + e]];
+#endif
+        ctx.sync();
+        pt.stop(PROF_FACTOR_BIG_STAGE);
+        const int ntI = ldy >> 2, ntJ = (w + 3) >> 2;
+        PAR_FOR(tile, ntI * ntJ) {
+            const int ti = tile % ntI, tj = tile / ntI;
+            if (4 * ti + 3 >= 4 * tj) {
+                double acc[4][4];
+#if CB_ON_DEVICE
+#pragma unroll
+#endif
+                for (int r = 0; r < 4; r++)
+#if CB_ON_DEVICE
+#pragma unroll
+#endif
+                    for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
+                const double *ya = Y + 4 * ti, *yb = Y + 4 * tj;
+                for (int cc = 0; cc < kc; cc++) {
+                    const double dcc = Dy[cc];
+                    double a[4], b[4];
+#if CB_ON_DEVICE
+                    const double2 a01 = *reinterpret_cast<const double2 *>(ya + cc * ldy);
+                    const double2 a23 = *reinterpret_cast<const double2 *>(ya + cc * ldy + 2);
+                    const double2 b01 = *reinterpret_cast<const double2 *>(yb + cc * ldy);
+                    const double2 b23 = *reinterpret_cast<const double2 *>(yb + cc * ldy + 2);
+                    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+                    b[0] = b01.x * dcc; b[1] = b01.y * dcc; b[2] = b23.x * dcc; b[3] = b23.y * dcc;
+#pragma unroll
+#else
+                    for (int r = 0; r < 4; r++) { a[r] = ya[r + cc * ldy]; b[r] = yb[r + cc * ldy] * dcc; }
+#endif
+                    for (int r = 0; r < 4; r++)
+#if CB_ON_DEVICE
+#pragma unroll
+#endif
+                        for (int q = 0; q < 4; q++) acc[r][q] += a[r] * b[q];
+                }
+#if CB_ON_DEVICE
+#pragma unroll
+#endif
+                for (int q = 0; q < 4; q++)
+#if CB_ON_DEVICE
+#pragma unroll
+#endif
+                    for (int r = 0; r < 4; r++) {
+                        const int Ii = 4 * ti + r, Jj = 4 * tj + q;
+                        if (Ii < nrow && Jj < w && Ii >= Jj) S[Ii + Jj * ldp] -= acc[r][q];
+                    }
+            }
+        }
+        ctx.sync();
+        pt.stop(PROF_FACTOR_BIG_GEMM);
+    }
+#if CB_ON_DEVICE
+    {
+        double *pivbuf = Y;              // 2 * NB doubles
+        double *dd = Y + 32;             // w doubles
+        __syncthreads();
+        if (ldp <= (int)blockDim.x) panel_factor_smem<8>(S, ldp, w, ldp, pivbuf, dd);
+        else panel_factor(ctx, S, ldp, w, ldp);
+    }
+#else
+    panel_factor(ctx, S, ldp, w, ldp);
+#endif
+    // write back: factor panel, pivots, and the solve block [M | LR] with odd leading dimensions
+    double *Mblk = Tinv + bt.tinv_off, *LR = Mblk + (long long)bt.ldm * w;
+#if CB_ON_DEVICE
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int k = wid; k < w; k += nw) {
+            const double *src = S + k * ldp;
+            for (int i = lane; i < nrow; i += 32) Ps[i + k * nrow] = src[i];
+            for (int i = lane; i < w; i += 32) Mblk[i + k * bt.ldm] = src[nrow + i];
+            for (int i = lane; i < nR; i += 32) LR[i + k * bt.ldr] = src[w + i];
+        }
+    }
+#else
+    PAR_FOR(e, nrow * w) {
+        int k = e / nrow, i = e % nrow;
+        Ps[e] = S[i + (long long)k * ldp];
+    }
+    PAR_FOR(e, w * w) {
+        int k = e / w, i = e % w;
+        Mblk[i + (long long)k * bt.ldm] = S[nrow + i + (long long)k * ldp];
+    }
+    PAR_FOR(e, nR * w) {
+        int k = e / nR, i = e % nR;
+        LR[i + (long long)k * bt.ldr] = S[w + i + (long long)k * ldp];
+    }
+#endif
+    PAR_FOR(k, w) {
+        double dk = S[k + (long long)k * ldp];
+        D[c0 + k] = dk;
+        Dinv[c0 + k] = dk != 0.0 ? 1.0 / dk : 0.0;
+    }
+    ctx.sync();
+    pt.stop(PROF_FACTOR_BIG_PANEL);
 }
 
 #if CB_ON_DEVICE
@@ -473,8 +774,9 @@ CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, d
 #define CB_CTA_SYNC()
 #endif
 
-// run f(scope, supernode) over the level schedule (forward = leaves first)
-template <class F> CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward, F f)
+// Run the level schedule (forward = leaves first): f(scope, supernode) for warp-/CTA-scope supernodes and
+// g(cta, begin, end) for a phase of singleton leaves (range in P.order).
+template <class F, class G> CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward, F f, G g)
 {
     Ctx wctx = cta;
 #if CB_ON_DEVICE
@@ -484,7 +786,9 @@ template <class F> CB_DEV void for_each_supernode(const Ctx &cta, const DevProbl
 #endif
     for (int pi = 0; pi < P.nphases; pi++) {
         const Phase ph = P.phases[forward ? pi : P.nphases - 1 - pi];
-        if (ph.mode == 1) {
+        if (ph.mode == 2) {
+            g(cta, ph.begin, ph.end);
+        } else if (ph.mode == 1) {
             for (int q = ph.begin; q < ph.end; q++) f(cta, P.order[q]);
         } else {
             for (int q = ph.begin + CB_WARP_ID; q < ph.end; q += CB_NUM_WARPS) f(wctx, P.order[q]);
@@ -494,9 +798,42 @@ template <class F> CB_DEV void for_each_supernode(const Ctx &cta, const DevProbl
 }
 
 // numeric factorisation + inertia (positive = #(D>0), negative = #(D<=0), zero = #(D==0); linear_solver.jl:33-44)
-CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, int *istat)
+CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, double *Tinv,
+                        double *Lcsr, int *istat, long long *prof)
 {
-    for_each_supernode(ctx, P, true, [&](const Ctx &c, int s) { factor_supernode(c, P, pan, D, Dinv, s); });
+    ProfTimer pt{prof, 0};
+    pt.start();
+    for_each_supernode(
+        ctx, P, true,
+        [&](const Ctx &c, int s) {
+            const int bi = (c.warp_scope || !P.big_index) ? -1 : P.big_index[s];
+            if (bi >= 0 && c.scratch) {
+                factor_supernode_big(c, P, pan, D, Dinv, Tinv, s, P.big[bi], pt);
+            } else {
+                factor_supernode(c, P, pan, D, Dinv, s);
+                if (!c.warp_scope) pt.stop(PROF_FACTOR_BIG_GENERIC);
+            }
+        },
+        [&](const Ctx &ctx, int begin, int end) {   // singleton leaves: L = a / d
+            pt.stop(PROF_FACTOR_SMALL);
+            PAR_FOR(q, end - begin) {
+                const int s = P.order[begin + q], c0 = P.sn_start[s];
+                const int nrow = 1 + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
+                double *Ps = pan + P.panel_off[s];
+                const int *pos = P.leaf_csr_pos + P.rows_ptr[s];
+                const double dk = Ps[0], dinv = dk != 0.0 ? 1.0 / dk : 0.0;
+                for (int i = 1; i < nrow; i++) {
+                    const double l = Ps[i] * dinv;
+                    Ps[i] = l;
+                    Lcsr[pos[i - 1]] = l;     // row-ordered copy for the bulk forward pass
+                }
+                D[c0] = dk;
+                Dinv[c0] = dinv;
+            }
+            ctx.sync();
+            pt.stop(PROF_FACTOR_LEAVES);
+        });
+    pt.stop(PROF_FACTOR_SMALL);
     double pos = scope_sum(ctx, P.N, [&](int i) { return D[i] > 0.0 ? 1.0 : 0.0; });
     double zer = scope_sum(ctx, P.N, [&](int i) { return D[i] == 0.0 ? 1.0 : 0.0; });
     if (ctx.tid == 0) {
@@ -506,62 +843,375 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
         istat[I_FACTORIZATIONS]++;
     }
     ctx.sync();
+    pt.stop(PROF_INERTIA);
 }
 
-// x = P' L^-T D^-1 L^-1 P b; b and x are in natural order (may alias), xp is an N-vector of scratch
-CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, const double *Dinv, const double *b,
-                       double *x, double *xp, int *istat)
+#if CB_ON_DEVICE
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+#if CB_ON_DEVICE
+// Fast path of ldl_solve (same arithmetic): the permuted vector lives in shared memory for the whole solve and the
+// chain of shared-memory supernodes streams its solve blocks [M | LR] through two shared-memory buffers filled by
+// TMA bulk copies one stage ahead (mbarrier complete_tx), so no global-memory latency sits on the critical path of
+// the elimination-tree chain.  Work area: xs[N] | buf0 | buf1 | 2 mbarriers | tmp[w].
+__device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P, const double *pan, const double *D,
+                                            const double *Dinv, const double *Tinv, const double *Lcsr,
+                                            const double *b, double *x, int *istat, long long *prof)
+{
+    ProfTimer pt{prof, 0};
+    pt.start();
+    const int N = P.N, Npad = (N + 1) & ~1;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double *xs = ctx.scratch;
+    double *buf[2] = {xs + Npad, xs + Npad + P.max_sb_doubles};
+    unsigned long long *bars = ctx.bars;
+    double *tmpv = buf[1] + P.max_sb_doubles;
+    for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
+    __syncthreads();
+    // the barriers live for the whole kernel: continue the issue/consume numbering where the previous solve stopped
+    unsigned issued = *ctx.bar_uses, consumed = issued;
+    const int *seq = P.big_seq;
+    auto issue = [&](int seq_idx) {    // called by all threads after a CTA barrier; thread 0 launches the copy
+        if (tid == 0) {
+            const BigTarget bt = P.big[P.big_index[seq[seq_idx]]];
+            const unsigned bytes = (unsigned)bt.sb_doubles * 8u;
+            const int slot = issued & 1;
+            fence_proxy_async();
+            mbar_expect_tx(&bars[slot], bytes);
+            tma_bulk_g2s(buf[slot], Tinv + bt.tinv_off, bytes, &bars[slot]);
+        }
+        issued++;
+    };
+    auto acquire = [&]() -> const double * {
+        const int slot = consumed & 1;
+        mbar_wait(&bars[slot], (unsigned)((consumed >> 1) & 1));
+        consumed++;
+        return buf[slot];
+    };
+    if (P.nbig > 0) issue(0);
+    // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final)
+    for (int cidx = tid; cidx < N; cidx += nthr) {
+        const int q0 = P.lcsr_ptr[cidx], q1 = P.lcsr_ptr[cidx + 1];
+        if (q1 > q0) {
+            double a0 = 0.0, a1 = 0.0;
+            int q = q0;
+            for (; q + 1 < q1; q += 2) {
+                a0 += Lcsr[q] * xs[P.lcsr_col[q]];
+                a1 += Lcsr[q + 1] * xs[P.lcsr_col[q + 1]];
+            }
+            if (q < q1) a0 += Lcsr[q] * xs[P.lcsr_col[q]];
+            xs[cidx] -= a0 + a1;
+        }
+    }
+    __syncthreads();
+    int pos = 0;
+    for_each_supernode(
+        ctx, P, true,
+        [&](const Ctx &c, int s) {
+            const Ctx &ctx = c;
+            const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+            const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
+            const int bi = c.warp_scope ? -1 : P.big_index[s];
+            PAR_FOR(j, w) {   // pull from small (non-leaf, non-shared-memory) descendants
+                double acc = 0.0;
+                for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
+                    const FwdEntry fe = P.fwd[q];
+                    const double *Ld = pan + fe.off;
+                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
+                }
+                if (acc != 0.0) xs[c0 + j] -= acc;
+            }
+            if (bi >= 0) {
+                const BigTarget bt = P.big[bi];
+                const int *R = P.rows + P.rows_ptr[s];
+                if (pos + 1 < P.nbig) issue(pos + 1);
+                const double *M = acquire(), *LR = M + bt.ldm * w;
+                pos++;
+                __syncthreads();
+                if (tid < w) {      // y_k = D_k sum_{i<=k} M[i,k] v_i
+                    const double *col = M + tid * bt.ldm;
+                    double a0 = 0.0, a1 = 0.0;
+                    int i = 0;
+                    for (; i + 1 <= tid; i += 2) { a0 += col[i] * xs[c0 + i]; a1 += col[i + 1] * xs[c0 + i + 1]; }
+                    if (i <= tid) a0 += col[i] * xs[c0 + i];
+                    tmpv[tid] = (a0 + a1) * D[c0 + tid];
+                }
+                __syncthreads();
+                if (tid < w) xs[c0 + tid] = tmpv[tid];
+                if (tid >= 64 && tid - 64 < nR) {   // push x[R] -= LR y  (a different warp set than the copy above)
+                    const int i = tid - 64;
+                    double a0 = 0.0, a1 = 0.0;
+                    int k = 0;
+                    for (; k + 1 < w; k += 2) { a0 += LR[i + k * bt.ldr] * tmpv[k]; a1 += LR[i + (k + 1) * bt.ldr] * tmpv[k + 1]; }
+                    if (k < w) a0 += LR[i + k * bt.ldr] * tmpv[k];
+                    xs[R[i]] -= a0 + a1;
+                }
+                if ((int)blockDim.x - 64 < nR) {    // more rows than spare threads: finish with a strided loop
+                    for (int i = (int)blockDim.x - 64 + tid; i < nR; i += nthr) {
+                        double a0 = 0.0;
+                        for (int k = 0; k < w; k++) a0 += LR[i + k * bt.ldr] * tmpv[k];
+                        xs[R[i]] -= a0;
+                    }
+                }
+                __syncthreads();
+                return;
+            }
+            const double *Ps = pan + P.panel_off[s];
+            for (int k = 0; k + 1 < w; k++) {
+                ctx.sync();
+                const double xk = xs[c0 + k];
+                PAR_FOR(i, w - 1 - k) xs[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
+            }
+            ctx.sync();
+        },
+        [&](const Ctx &, int, int) {});
+    for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
+    __syncthreads();
+    pt.stop(PROF_SOLVE_FWD);
+    pos = 0;
+    seq = P.big_seq_bwd;
+    if (P.nbig > 0) issue(0);
+    for_each_supernode(
+        ctx, P, false,
+        [&](const Ctx &c, int s) {
+            const Ctx &ctx = c;
+            const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+            const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
+            const double *Ps = pan + P.panel_off[s];
+            const int *R = P.rows + P.rows_ptr[s];
+            const int bi = c.warp_scope ? -1 : P.big_index[s];
+            if (bi >= 0) {
+                const BigTarget bt = P.big[bi];
+                if (pos + 1 < P.nbig) issue(pos + 1);
+                const double *M = acquire(), *LR = M + bt.ldm * w;
+                pos++;
+                if (tid < w) {      // dv_k = D_k (x_k - sum_i LR[i,k] x[R_i])
+                    const double *col = LR + tid * bt.ldr;
+                    double a0 = 0.0, a1 = 0.0;
+                    int i = 0;
+                    for (; i + 1 < nR; i += 2) { a0 += col[i] * xs[R[i]]; a1 += col[i + 1] * xs[R[i + 1]]; }
+                    if (i < nR) a0 += col[i] * xs[R[i]];
+                    tmpv[tid] = (xs[c0 + tid] - (a0 + a1)) * D[c0 + tid];
+                }
+                __syncthreads();
+                if (tid < w) {      // x_i = sum_{k>=i} M[i,k] dv_k
+                    double a0 = 0.0, a1 = 0.0;
+                    int k = tid;
+                    for (; k + 1 < w; k += 2) { a0 += M[tid + k * bt.ldm] * tmpv[k]; a1 += M[tid + (k + 1) * bt.ldm] * tmpv[k + 1]; }
+                    if (k < w) a0 += M[tid + k * bt.ldm] * tmpv[k];
+                    xs[c0 + tid] = a0 + a1;
+                }
+                __syncthreads();
+                return;
+            }
+            PAR_FOR(k, w) {
+                double acc = 0.0;
+                const double *col = Ps + (long long)k * nrow + w;
+                for (int i = 0; i < nR; i++) acc += col[i] * xs[R[i]];
+                xs[c0 + k] -= acc;
+            }
+            for (int k = w - 1; k > 0; k--) {
+                ctx.sync();
+                const double xk = xs[c0 + k];
+                PAR_FOR(i, k) xs[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
+            }
+            ctx.sync();
+        },
+        [&](const Ctx &ctx, int begin, int end) {
+            PAR_FOR(q, end - begin) {
+                const int s = P.order[begin + q], c0 = P.sn_start[s];
+                const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];
+                const double *col = pan + P.panel_off[s] + 1;
+                const int *R = P.rows + P.rows_ptr[s];
+                double a0 = 0.0, a1 = 0.0;
+                int i = 0;
+                for (; i + 1 < nR; i += 2) { a0 += col[i] * xs[R[i]]; a1 += col[i + 1] * xs[R[i + 1]]; }
+                if (i < nR) a0 += col[i] * xs[R[i]];
+                xs[c0] -= a0 + a1;
+            }
+            ctx.sync();
+        });
+    for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
+    if (tid == 0 && istat) istat[I_SOLVES]++;
+    __syncthreads();
+    if (tid == 0) *ctx.bar_uses = issued;
+    __syncthreads();
+    pt.stop(PROF_SOLVE_BWD);
+}
+#endif
+
+// x = P' L^-T D^-1 L^-1 P b; b and x are in natural order (may alias), xp is an N-vector of scratch.
+// Supernodes on the shared-memory path use M = L_tt^-T D_t^-1 (stored by the factorisation) so that their triangular
+// solves are mat-vecs: forward y_t = D_t M' v, backward x_t = M (D_t v).
+CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, const double *D, const double *Dinv,
+                       const double *Tinv, const double *Lcsr, const double *b, double *x, double *xp, int *istat,
+                       long long *prof)
+{
+#if CB_ON_DEVICE
+    if (P.solve_smem && ctx.scratch && blockDim.x >= 128) {
+        ldl_solve_smem(ctx, P, pan, D, Dinv, Tinv, Lcsr, b, x, istat, prof);
+        return;
+    }
+#endif
+    ProfTimer pt{prof, 0};
+    pt.start();
     PAR_FOR(k, P.N) xp[k] = b[P.perm[k]];
     ctx.sync();
-    // forward: pull from descendants through the per-column row lists, then the unit-lower diagonal block
-    for_each_supernode(ctx, P, true, [&](const Ctx &c, int s) {
-        const Ctx &ctx = c;
-        const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
-        const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
-        const double *Ps = pan + P.panel_off[s];
-        PAR_FOR(j, w) {
+    // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final)
+    PAR_FOR(cidx, P.N) {
+        const int q0 = P.lcsr_ptr[cidx], q1 = P.lcsr_ptr[cidx + 1];
+        if (q1 > q0) {
             double acc = 0.0;
-            for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
-                const int d = P.fwd_d[q], cd0 = P.sn_start[d], wd = P.sn_start[d + 1] - cd0;
-                const int nrowd = wd + (P.rows_ptr[d + 1] - P.rows_ptr[d]);
-                const double *Ld = pan + P.panel_off[d] + P.fwd_row[q];
-                for (int k = 0; k < wd; k++) acc += Ld[(long long)k * nrowd] * xp[cd0 + k];
+            for (int q = q0; q < q1; q++) acc += Lcsr[q] * xp[P.lcsr_col[q]];
+            xp[cidx] -= acc;
+        }
+    }
+    ctx.sync();
+    // forward: pull from descendants through the per-column row lists, then the unit-lower diagonal block
+    for_each_supernode(
+        ctx, P, true,
+        [&](const Ctx &c, int s) {
+            const Ctx &ctx = c;
+            const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+            const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
+            const double *Ps = pan + P.panel_off[s];
+            const int bi = (c.warp_scope || !P.big_index || !c.scratch) ? -1 : P.big_index[s];
+            if (bi >= 0) {
+                // shared-memory supernode: pull from small descendants, y = D M' v, then PUSH  x[R] -= LR y
+                const BigTarget bt = P.big[bi];
+                const int nR = nrow - w;
+                const int *R = P.rows + P.rows_ptr[s];
+                const double *M = Tinv + bt.tinv_off, *LR = M + (long long)bt.ldm * w;
+                double *y = ctx.scratch;
+                PAR_FOR(j, w) {
+                    double acc = 0.0;
+                    for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
+                        const FwdEntry fe = P.fwd[q];
+                        const double *Ld = pan + fe.off;
+                        for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
+                    }
+                    xp[c0 + j] -= acc;
+                }
+                ctx.sync();
+                PAR_FOR(k, w) {
+                    double acc = 0.0;
+                    const double *col = M + (long long)k * bt.ldm;
+                    for (int i = 0; i <= k; i++) acc += col[i] * xp[c0 + i];
+                    y[k] = acc * D[c0 + k];
+                }
+                ctx.sync();
+                PAR_FOR(k, w) xp[c0 + k] = y[k];
+                PAR_FOR(i, nR) {
+                    double acc = 0.0;
+                    for (int k = 0; k < w; k++) acc += LR[i + (long long)k * bt.ldr] * y[k];
+                    xp[R[i]] -= acc;
+                }
+                ctx.sync();
+                return;
             }
-            xp[c0 + j] -= acc;
-        }
-        for (int k = 0; k + 1 < w; k++) {
+            PAR_FOR(j, w) {
+                double acc = 0.0;
+                for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
+                    const FwdEntry fe = P.fwd[q];
+                    const double *Ld = pan + fe.off;
+                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
+                }
+                xp[c0 + j] -= acc;
+            }
+            for (int k = 0; k + 1 < w; k++) {
+                ctx.sync();
+                const double xk = xp[c0 + k];
+                PAR_FOR(i, w - 1 - k) xp[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
+            }
             ctx.sync();
-            const double xk = xp[c0 + k];
-            PAR_FOR(i, w - 1 - k) xp[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
-        }
-        ctx.sync();
-    });
+        },
+        [&](const Ctx &, int, int) {});   // singleton leaves have nothing to pull and no diagonal block
     PAR_FOR(k, P.N) xp[k] *= Dinv[k];
     ctx.sync();
+    pt.stop(PROF_SOLVE_FWD);
     // backward: gather from the ancestors' (already final) entries, then the unit-upper diagonal block
-    for_each_supernode(ctx, P, false, [&](const Ctx &c, int s) {
-        const Ctx &ctx = c;
-        const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
-        const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
-        const double *Ps = pan + P.panel_off[s];
-        const int *R = P.rows + P.rows_ptr[s];
-        PAR_FOR(k, w) {
-            double acc = 0.0;
-            const double *col = Ps + (long long)k * nrow + w;
-            for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
-            xp[c0 + k] -= acc;
-        }
-        for (int k = w - 1; k > 0; k--) {
+    for_each_supernode(
+        ctx, P, false,
+        [&](const Ctx &c, int s) {
+            const Ctx &ctx = c;
+            const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+            const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
+            const double *Ps = pan + P.panel_off[s];
+            const int *R = P.rows + P.rows_ptr[s];
+            const int bi = (c.warp_scope || !P.big_index || !c.scratch) ? -1 : P.big_index[s];
+            if (bi >= 0) {
+                // x_t = M (D (Dinv y_t - LR' x_R))
+                const BigTarget bt = P.big[bi];
+                const double *M = Tinv + bt.tinv_off, *LR = M + (long long)bt.ldm * w;
+                double *dv = ctx.scratch;
+                PAR_FOR(k, w) {
+                    double acc = 0.0;
+                    const double *col = LR + (long long)k * bt.ldr;
+                    for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
+                    dv[k] = (xp[c0 + k] - acc) * D[c0 + k];
+                }
+                ctx.sync();
+                PAR_FOR(i, w) {
+                    double acc = 0.0;
+                    for (int k = i; k < w; k++) acc += M[i + (long long)k * bt.ldm] * dv[k];
+                    xp[c0 + i] = acc;
+                }
+                ctx.sync();
+                return;
+            }
+            PAR_FOR(k, w) {
+                double acc = 0.0;
+                const double *col = Ps + (long long)k * nrow + w;
+                for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
+                xp[c0 + k] -= acc;
+            }
+            for (int k = w - 1; k > 0; k--) {
+                ctx.sync();
+                const double xk = xp[c0 + k];
+                PAR_FOR(i, k) xp[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
+            }
             ctx.sync();
-            const double xk = xp[c0 + k];
-            PAR_FOR(i, k) xp[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
-        }
-        ctx.sync();
-    });
+        },
+        [&](const Ctx &ctx, int begin, int end) {
+            PAR_FOR(q, end - begin) {
+                const int s = P.order[begin + q], c0 = P.sn_start[s];
+                const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];
+                const double *col = pan + P.panel_off[s] + 1;
+                const int *R = P.rows + P.rows_ptr[s];
+                double acc = 0.0;
+                for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
+                xp[c0] -= acc;
+            }
+            ctx.sync();
+        });
     PAR_FOR(k, P.N) x[P.perm[k]] = xp[k];
     if (ctx.tid == 0 && istat) istat[I_SOLVES]++;
     ctx.sync();
+    pt.stop(PROF_SOLVE_BWD);
 }
 
 // ------------------------------------------------------------------------------------------------ reduced rhs / recovery
@@ -681,8 +1331,11 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
 // factorize_regularized_residual_jacobian_variables!  inertia.jl:13-28
 CB_DEV bool factorize_regularized(const Ctx &ctx, const DevProblem &P, const Inst &I)
 {
+    ProfTimer pt{I.prof, 0};
+    pt.start();
     kkt_assemble(ctx, P, I);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.istat);
+    pt.stop(PROF_ASSEMBLE);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, I.prof);
     bool ok = I.istat[I_INERTIA_POS] == P.n && I.istat[I_INERTIA_NEG] == P.m + P.p && I.istat[I_INERTIA_ZERO] == 0;
     ctx.sync();
     if (ctx.tid == 0) I.istat[I_TRIALS]++;
@@ -726,17 +1379,26 @@ CB_DEVN int inertia_correction(const Ctx &ctx, const DevProblem &P, const Inst &
 // SURVEY.md Appendix A.7)
 CB_DEV void direction_symmetric(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *res, double *step)
 {
+    ProfTimer pt{I.prof, 0};
+    pt.start();
     reduced_rhs(ctx, P, I, res, I.rs);
-    ldl_solve(ctx, P, I.panels, I.Dinv, I.rs, I.xs, I.xp, I.istat);
+    pt.stop(PROF_RHS_RECOVER);
+    ldl_solve(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.rs, I.xs, I.xp, I.istat, I.prof);
+    pt.start();
     recover_step(ctx, P, I, res, I.xs, step);
+    pt.stop(PROF_RHS_RECOVER);
 }
 
 CB_DEV double residual_error(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *step)
 {   // err = R - J step, returns its infinity norm
+    ProfTimer pt{I.prof, 0};
+    pt.start();
     jacobian_times(ctx, P, I, step, I.tmp);
     PAR_FOR(i, P.total) I.err[i] = I.res[i] - I.tmp[i];
     ctx.sync();
-    return scope_max(ctx, P.total, [&](int i) { return fabs(I.err[i]); });
+    double r = scope_max(ctx, P.total, [&](int i) { return fabs(I.err[i]); });
+    pt.stop(PROF_JTIMES);
+    return r;
 }
 
 // iterative_refinement!  iterative_refinement.jl:1-53

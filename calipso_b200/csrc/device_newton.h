@@ -173,6 +173,9 @@ CB_DEVN int newton_iteration_lq(const Ctx &ctx, const DevProblem &P, const Inst 
 {
     const int n = P.n, m = P.m, p = P.p, N = P.N;
     double *w = I.w;
+    ProfTimer pt{I.prof, 0}, ptot{I.prof, 0};
+    pt.start();
+    ptot.start();
     lq_evaluate(ctx, P, I, w, EV_GRADIENT | EV_EQUALITY_DUAL_GRAD | EV_CONE_DUAL_GRAD);
     cone_eval(ctx, P, I, w, 1, 1, 0);
     const double M = merit_value(ctx, P, I, w);
@@ -186,9 +189,11 @@ CB_DEVN int newton_iteration_lq(const Ctx &ctx, const DevProblem &P, const Inst 
     else if (I.scal[S_OPTIMALITY_VIOLATION] <= fmax(o.central_path_update_tolerance * kappa, o.optimality_tolerance))
         return 2;
     const double theta = constraint_violation(ctx, P, I, w);
+    pt.stop(PROF_CONE_RESIDUAL);
     // (second derivatives and Jacobians are constant for the LQ family: nothing to re-evaluate, solve.jl:175-185)
     int st = search_direction(ctx, P, I, o);
     if (st == ST_INERTIA_FAILURE) return -ST_INERTIA_FAILURE;
+    pt.start();
     st = cone_search(ctx, P, I, o);
     if (st != ST_OK) return -ST_CONE_SEARCH_FAILURE;
     double step_size = I.scal[S_STEP_SIZE];
@@ -246,6 +251,8 @@ CB_DEVN int newton_iteration_lq(const Ctx &ctx, const DevProblem &P, const Inst 
         I.istat[I_INNER]++;
     }
     ctx.sync();
+    pt.stop(PROF_EVAL_LINESEARCH);
+    ptot.stop(PROF_TOTAL);
     return 0;
 }
 

@@ -3,6 +3,7 @@
 // (src/solver/residual_jacobian_variables.jl:110-167, upper triangle as kept by triu!, linear_solver.jl:23), its
 // symbolic factorisation and the assembly destinations.  Pure C++; api.cu uploads the vectors to the device.
 #pragma once
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -120,6 +121,29 @@ struct HostProblem {
     }
 };
 
+// L in QDLDL's CSC form (true structure, explicit padding zeros dropped) from the supernodal panels of one instance
+inline void extract_factor(const Symbolic &S, const double *pan, int *Lp, int *Li, double *Lx)
+{
+    Lp[0] = 0;
+    for (int s = 0; s < S.ns; s++) {
+        const int c0 = S.sn_start[s], c1 = S.sn_start[s + 1], w = c1 - c0;
+        const int nR = S.rows_ptr[s + 1] - S.rows_ptr[s], nrow = w + nR;
+        const int *Rs = S.rows.data() + S.rows_ptr[s];
+        const double *Ps = pan + S.panel_off[s];
+        for (int c = c0; c < c1; c++) {
+            int k = Lp[c];
+            for (int q = S.Lptr[c]; q < S.Lptr[c + 1]; q++) {
+                const int r = S.Lrows[q];
+                const int lr = r < c1 ? r - c0 : w + (int)(std::lower_bound(Rs, Rs + nR, r) - Rs);
+                Li[k] = r;
+                Lx[k] = Ps[lr + (long long)(c - c0) * nrow];
+                k++;
+            }
+            Lp[c + 1] = k;
+        }
+    }
+}
+
 // Fill the pointer fields of a DevProblem from any provider `up(vector) -> const T*` (device upload or host data()).
 template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
 {
@@ -127,8 +151,14 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.panel_total = S.panel_total;
     P.perm = up(S.perm); P.sn_start = up(S.sn_start); P.rows_ptr = up(S.rows_ptr); P.rows = up(S.rows);
     P.panel_off = up(S.panel_off); P.upd_ptr = up(S.upd_ptr); P.upd = up(S.upd); P.rel = up(S.rel);
-    P.order = up(S.order); P.phases = up(S.phases); P.fwd_ptr = up(S.fwd_ptr); P.fwd_d = up(S.fwd_d);
-    P.fwd_row = up(S.fwd_row);
+    P.order = up(S.order); P.phases = up(S.phases); P.fwd_ptr = up(S.fwd_ptr); P.fwd = up(S.fwd);
+    P.big_index = up(S.big_index); P.big = up(S.big); P.ychunks = up(S.ychunks);
+    P.ystage_src = up(S.ystage_src); P.ystage_dst = up(S.ystage_dst); P.ypiv = up(S.ypiv);
+    P.tinv_total = S.tinv_total;
+    P.big_seq = up(S.big_seq); P.big_seq_bwd = up(S.big_seq_bwd); P.nbig = (int)S.big_seq.size(); P.max_sb_doubles = S.max_sb_doubles;
+    P.solve_smem = S.solve_smem;
+    P.lcsr_ptr = up(S.lcsr_ptr); P.lcsr_col = up(S.lcsr_col); P.leaf_csr_pos = up(S.leaf_csr_pos);
+    P.lcsr_total = S.lcsr_total;
 }
 
 template <class Up> void fill_problem(DevProblem &P, const HostProblem &H, Up up)

@@ -127,7 +127,8 @@ static void permuted_upper(int n, const int *Ap, const int *Ai, const std::vecto
         }
 }
 
-const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold)
+const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
+                              int smem_budget_doubles)
 {
     N = n;
     nnzA = Ap[n];
@@ -184,9 +185,9 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     flops = 0;
     for (int j = 0; j < n; j++) flops += (long long)Lnz[j] * Lnz[j];
     // 3. column structures of L: struct(j) = lower(A)_j U (struct(children) \ {j})
-    std::vector<int> Lptr(n + 1, 0);
+    Lptr.assign(n + 1, 0);
     for (int j = 0; j < n; j++) Lptr[j + 1] = Lptr[j] + Lnz[j];
-    std::vector<int> Lrows((size_t)Lptr[n]);
+    Lrows.assign((size_t)Lptr[n], 0);
     {
         // lower entries by column = upper entries by row: transpose Up/Ui
         std::vector<int> cnt(n + 1, 0);
@@ -220,17 +221,59 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             std::sort(out, out + k);
         }
     }
-    // 4. fundamental supernodes (consecutive columns, parent = next column, nested structure)
-    const int max_width = 128;
-    sn_start.clear();
-    sn_of.assign(n, 0);
+    // 4. fundamental supernodes (consecutive columns, parent = next column, nested structure) ...
+    const int max_width = 64;    // keeps (rows + width) x width panels inside the shared-memory budget
+    std::vector<int> fstart;
     for (int j = 0; j < n; j++) {
-        bool merge = j > 0 && etree[j - 1] == j && Lnz[j - 1] == Lnz[j] + 1 && (j - sn_start.back()) < max_width;
-        if (!merge) sn_start.push_back(j);
-        sn_of[j] = (int)sn_start.size() - 1;
+        bool merge = j > 0 && etree[j - 1] == j && Lnz[j - 1] == Lnz[j] + 1 && (j - fstart.back()) < max_width;
+        if (!merge) fstart.push_back(j);
     }
+    const int nf = (int)fstart.size();
+    fstart.push_back(n);
+    // ... then relaxed amalgamation: a supernode that has children of its own is merged into the supernode that
+    // follows it when that one holds its parent and the padding (explicit zeros) stays small.  Childless supernodes
+    // (the singleton leaves a minimum-degree ordering makes of the constraint rows) are never merged: they are
+    // processed in bulk.  Walk right to left so that a group keeps the row structure of its rightmost member.
+    std::vector<int> nchild(n, 0);
+    for (int j = 0; j < n; j++)
+        if (etree[j] >= 0) nchild[etree[j]]++;
+    std::vector<int> gstart;   // group starts, collected right to left
+    {
+        int cur_start = fstart[nf - 1], cur_end = n, cur_R = Lnz[n - 1];
+        long long cur_entries = 0, cur_zeros = 0;
+        for (int j = cur_start; j < cur_end; j++) cur_entries += (cur_end - 1 - j) + cur_R;
+        for (int f = nf - 2; f >= 0; f--) {
+            int a = fstart[f], b = fstart[f + 1];
+            bool can = etree[b - 1] >= cur_start && etree[b - 1] < cur_end && nchild[a] > 0 && (cur_end - a) <= max_width;
+            long long add_entries = 0, add_zeros = 0;
+            if (can) {
+                for (int j = a; j < b; j++) {
+                    long long padded = (cur_end - 1 - j) + cur_R;
+                    add_entries += padded;
+                    add_zeros += padded - Lnz[j];
+                }
+                long long z = cur_zeros + add_zeros, e = cur_entries + add_entries;
+                can = z <= 16 || z * 10 <= e;   // at most 10% explicit zeros
+            }
+            if (can) {
+                cur_start = a;
+                cur_entries += add_entries;
+                cur_zeros += add_zeros;
+            } else {
+                gstart.push_back(cur_start);
+                cur_start = a; cur_end = b; cur_R = Lnz[b - 1];
+                cur_entries = 0; cur_zeros = 0;
+                for (int j = a; j < b; j++) cur_entries += (b - 1 - j) + cur_R;
+            }
+        }
+        gstart.push_back(cur_start);
+    }
+    sn_start.assign(gstart.rbegin(), gstart.rend());
     ns = (int)sn_start.size();
     sn_start.push_back(n);
+    sn_of.assign(n, 0);
+    for (int s = 0; s < ns; s++)
+        for (int j = sn_start[s]; j < sn_start[s + 1]; j++) sn_of[j] = s;
     rows_ptr.assign(ns + 1, 0);
     panel_off.assign(ns + 1, 0);
     max_w = max_nrow = 0;
@@ -288,25 +331,6 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         for (auto &u : lists[t]) upd.push_back(u);
         upd_ptr[t + 1] = (int)upd.size();
     }
-    // 5b. forward-solve row lists (row c of L, grouped by the supernode that stores it)
-    fwd_ptr.assign(n + 1, 0);
-    for (int d = 0; d < ns; d++)
-        for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) fwd_ptr[rows[q] + 1]++;
-    for (int c = 0; c < n; c++) fwd_ptr[c + 1] += fwd_ptr[c];
-    fwd_d.assign(fwd_ptr[n], 0);
-    fwd_row.assign(fwd_ptr[n], 0);
-    {
-        std::vector<int> nx(fwd_ptr.begin(), fwd_ptr.end() - 1);
-        for (int d = 0; d < ns; d++) {
-            int wd = sn_start[d + 1] - sn_start[d];
-            for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) {
-                int c = rows[q];
-                fwd_d[nx[c]] = d;
-                fwd_row[nx[c]] = wd + (q - rows_ptr[d]);
-                nx[c]++;
-            }
-        }
-    }
     // 6. levels and phases
     level.assign(ns, 0);
     nlevels = 0;
@@ -320,21 +344,132 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     }
     order.resize(ns);
     std::iota(order.begin(), order.end(), 0);
-    std::vector<char> big(ns);
-    for (int t = 0; t < ns; t++) big[t] = work[t] >= big_task_threshold;
+    // class of a supernode inside its level: 0 singleton leaf (width 1, nothing to pull), 1 big (CTA), 2 small (warp)
+    std::vector<char> cls(ns);
+    for (int t = 0; t < ns; t++) {
+        bool single_leaf = (sn_start[t + 1] - sn_start[t] == 1) && upd_ptr[t + 1] == upd_ptr[t];
+        cls[t] = single_leaf ? 0 : (work[t] >= big_task_threshold ? 1 : 2);
+    }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
         if (level[x] != level[y]) return level[x] < level[y];
-        if (big[x] != big[y]) return big[x] > big[y];
+        if (cls[x] != cls[y]) return cls[x] < cls[y];
         return x < y;
     });
     phases.clear();
     for (int i = 0; i < ns;) {
         int j = i;
-        while (j < ns && level[order[j]] == level[order[i]] && big[order[j]] == big[order[i]]) j++;
-        int mode = big[order[i]] ? 1 : 0;
-        if (!mode && j - i == 1) mode = 1;  // a lone small task: let the whole CTA help anyway
+        while (j < ns && level[order[j]] == level[order[i]] && cls[order[j]] == cls[order[i]]) j++;
+        int mode = cls[order[i]] == 0 ? 2 : (cls[order[i]] == 1 ? 1 : 0);
+        if (mode == 0 && j - i == 1) mode = 1;  // a lone small task: let the whole CTA help anyway
         phases.push_back(Phase{mode, i, j});
         i = j;
+    }
+    // 6b. shared-memory staging plan for CTA-scope targets
+    big_index.assign(ns, -1);
+    big.clear(); ychunks.clear(); ystage_src.clear(); ystage_dst.clear(); ypiv.clear(); big_seq.clear();
+    max_sb_doubles = 0;
+    tinv_total = 0;
+    scratch_doubles = 0;
+    for (const Phase &ph : phases) {
+        if (ph.mode != 1 || panel_total > 2000000000LL) continue;
+        for (int q = ph.begin; q < ph.end; q++) {
+            int t = order[q];
+            int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
+            int ldy = (nrow + 3) & ~3;
+            long long panel_d = ((long long)(nrow + w) * w + 1) & ~1LL;   // panel + w identity rows (-> M = L^-T D^-1)
+            long long tinv_d = ((long long)w * w + 1) & ~1LL;
+            long long fixed = panel_d;
+            int ktot = 0;
+            for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) ktot += sn_start[upd[u].d + 1] - sn_start[upd[u].d];
+            if (fixed + (ktot > 0 ? (long long)(ldy + 1) * 8 : 0) > smem_budget_doubles) continue;   // generic path
+            int kc_max = ktot > 0 ? (int)std::min<long long>((smem_budget_doubles - fixed) / (ldy + 1), ktot) : 0;
+            BigTarget bt;
+            bt.chunk_begin = (int)ychunks.size();
+            bt.ldy = ldy;
+            bt.tinv_off = (int)tinv_total;
+            bt.ldm = w | 1;
+            bt.ldr = (nrow - w) | 1;
+            bt.sb_doubles = (int)(((long long)(bt.ldm + bt.ldr) * w + 1) & ~1LL);
+            tinv_total += bt.sb_doubles;
+            (void)tinv_d;
+            int col = 0;
+            YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size()};
+            int max_kc = 0;
+            for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) {
+                const UpdateEntry &ue = upd[u];
+                int cd0 = sn_start[ue.d], wd = sn_start[ue.d + 1] - cd0;
+                int nRd = rows_ptr[ue.d + 1] - rows_ptr[ue.d], nrowd = wd + nRd;
+                for (int k = 0; k < wd; k++) {
+                    if (col - ch.col_begin == kc_max) {   // chunk full
+                        ch.col_end = col; ch.stage_end = (int)ystage_src.size();
+                        max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
+                        ychunks.push_back(ch);
+                        ch = YChunk{col, col, (int)ystage_src.size(), 0, (int)ypiv.size()};
+                    }
+                    ypiv.push_back(cd0 + k);
+                    for (int i = ue.a; i < nRd; i++) {
+                        ystage_src.push_back((int)(panel_off[ue.d] + (wd + i) + (long long)k * nrowd));
+                        ystage_dst.push_back(rel[ue.rel + (i - ue.a)] + (col - ch.col_begin) * ldy);
+                    }
+                    col++;
+                }
+            }
+            if (col > ch.col_begin) {
+                ch.col_end = col; ch.stage_end = (int)ystage_src.size();
+                max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
+                ychunks.push_back(ch);
+            }
+            bt.chunk_end = (int)ychunks.size();
+            big_index[t] = (int)big.size();
+            big.push_back(bt);
+            big_seq.push_back(t);
+            max_sb_doubles = std::max(max_sb_doubles, bt.sb_doubles);
+            scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>((long long)max_kc * (ldy + 1), 40 + w) + 8);
+        }
+    }
+    big_seq_bwd.clear();
+    for (int pi = (int)phases.size() - 1; pi >= 0; pi--)
+        if (phases[pi].mode == 1)
+            for (int q = phases[pi].begin; q < phases[pi].end; q++)
+                if (big_index[order[q]] >= 0) big_seq_bwd.push_back(order[q]);
+    {   // shared-memory solve: x (N padded to even) + two solve-block buffers + barriers
+        long long need = ((long long)N + 1) / 2 * 2 + 2LL * max_sb_doubles + 16 + 2 * max_width + 16;
+        solve_smem = (!big.empty() && need <= smem_budget_doubles) ? 1 : 0;
+        if (solve_smem) scratch_doubles = (int)std::max<long long>(scratch_doubles, need);
+    }
+    // 6c. forward-solve row lists (row c of L, grouped by the supernode that stores it); singleton leaves apart,
+    //     shared-memory (big) supernodes excluded: they push
+    auto is_single_leaf = [&](int d) { return cls[d] == 0; };
+    fwd_ptr.assign(n + 1, 0);
+    lcsr_ptr.assign(n + 1, 0);
+    for (int d = 0; d < ns; d++) {
+        bool leaf = is_single_leaf(d);
+        if (!leaf && big_index[d] >= 0) continue;   // shared-memory supernodes PUSH their forward updates
+        for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) (leaf ? lcsr_ptr : fwd_ptr)[rows[q] + 1]++;
+    }
+    for (int c = 0; c < n; c++) { fwd_ptr[c + 1] += fwd_ptr[c]; lcsr_ptr[c + 1] += lcsr_ptr[c]; }
+    fwd.assign(fwd_ptr[n], FwdEntry{0, 0, 0, 0});
+    lcsr_col.assign(lcsr_ptr[n], 0);
+    leaf_csr_pos.assign(rows.size(), -1);
+    lcsr_total = lcsr_ptr[n];
+    {
+        std::vector<int> nx(fwd_ptr.begin(), fwd_ptr.end() - 1), nl(lcsr_ptr.begin(), lcsr_ptr.end() - 1);
+        for (int d = 0; d < ns; d++) {
+            int wd = sn_start[d + 1] - sn_start[d];
+            int nrowd = wd + rows_ptr[d + 1] - rows_ptr[d];
+            bool leaf = is_single_leaf(d);
+            for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) {
+                int c = rows[q];
+                if (leaf) {
+                    lcsr_col[nl[c]] = sn_start[d];
+                    leaf_csr_pos[q] = nl[c];
+                    nl[c]++;
+                } else if (big_index[d] < 0) {
+                    fwd[nx[c]] = FwdEntry{(int)panel_off[d] + wd + (q - rows_ptr[d]), sn_start[d], wd, nrowd};
+                    nx[c]++;
+                }
+            }
+        }
     }
     // 7. destination of every input entry in the panel storage
     dest.assign(nnzA, 0);

@@ -19,8 +19,31 @@ struct UpdateEntry {
 };
 
 struct Phase {
-    int mode;        // 0: one warp per supernode (tasks run concurrently); 1: whole CTA per supernode (sequential)
+    int mode;        // 0: one warp per supernode (tasks run concurrently); 1: whole CTA per supernode (sequential);
+                     // 2: singleton leaves (width 1, no incoming update), one thread per supernode
     int begin, end;  // range in Symbolic::order
+};
+
+// A CTA-scope target whose panel fits in shared memory pulls ALL its descendants' columns at once: they are staged
+// as the columns of a dense (rows of the target) x (sum of descendant widths) matrix Y and applied as one GEMM
+// S -= Y diag(D) Y_top'.  Chunks bound the shared-memory footprint.
+struct YChunk {
+    int col_begin, col_end;      // Y columns of this chunk
+    int stage_begin, stage_end;  // range in ystage_src / ystage_dst
+    int piv_begin;               // ypiv[piv_begin + c]: pivot (permuted column) of chunk column c
+};
+struct BigTarget {
+    int chunk_begin, chunk_end;
+    int ldy;                     // leading dimension of Y (rows padded to a multiple of 4)
+    int tinv_off;                // offset of this supernode's solve block in the Tinv storage:
+                                 //   M  = L_tt^-T D_t^-1   (w x w,  leading dimension ldm, odd => bank-conflict free)
+                                 //   LR = L[R_t, t]        (nR x w, leading dimension ldr, odd), at tinv_off + ldm*w
+    int ldm, ldr;
+    int sb_doubles;              // ldm*w + ldr*w rounded up to even
+};
+struct FwdEntry {                // one (descendant, row) pair of the forward-solve row lists, flattened
+    int off;                     // panel offset of L_d[row, 0]
+    int col0, width, stride;     // first pivot column of d, its width, its panel leading dimension
 };
 
 struct Symbolic {
@@ -48,8 +71,28 @@ struct Symbolic {
     std::vector<int> order;       // supernodes sorted by (level, big-first)
     std::vector<Phase> phases;
     int nlevels = 0;
-    // forward-solve row lists: for permuted column c, the (descendant supernode, local panel row) pairs holding row c
-    std::vector<int> fwd_ptr, fwd_d, fwd_row;
+    // true (unpadded) column structure of L, for extracting the factor in QDLDL's CSC form
+    std::vector<int> Lptr, Lrows;
+    // forward-solve row lists: for permuted column c, the (descendant supernode, local panel row) pairs holding row c.
+    // Singleton-leaf descendants are kept apart: their contributions to every ancestor are known up front (x_leaf = b)
+    // and are pulled in one bulk pass from a row-ordered (CSR) copy of the leaf columns written by the factorisation.
+    std::vector<int> fwd_ptr;
+    std::vector<FwdEntry> fwd;       // non-leaf descendants only
+    std::vector<int> lcsr_ptr;       // [N+1] per permuted column: range in lcsr_col / the Lcsr value array
+    std::vector<int> lcsr_col;       // pivot column of the leaf
+    std::vector<int> leaf_csr_pos;   // [rows.size()] for entry q of rows[] of a singleton leaf: its position in Lcsr (-1 else)
+    long long lcsr_total = 0;
+    // shared-memory path for big targets
+    std::vector<int> big_index;   // [ns] index into big, or -1
+    std::vector<BigTarget> big;
+    std::vector<YChunk> ychunks;
+    std::vector<int> ystage_src, ystage_dst, ypiv;
+    std::vector<int> big_seq;     // shared-memory supernodes in forward schedule order (TMA prefetch chain)
+    std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
+    int max_sb_doubles = 0;       // largest solve block
+    int solve_smem = 0;           // 1: x and two solve-block buffers fit in the CTA work area (ldl_solve fast path)
+    long long tinv_total = 0;     // doubles of Tinv storage per instance
+    int scratch_doubles = 0;      // shared-memory doubles a CTA needs
     // input entry k of the upper-triangular CSC -> offset in the panel storage
     std::vector<long long> dest;
 
@@ -57,7 +100,8 @@ struct Symbolic {
     // user_perm (may be null): caller-specified elimination order, like qdldl(A; perm=p) (qdldl.jl:134-136); it is
     // still postordered (which does not change the fill) so that supernodes are contiguous.
     // Returns an empty string on success, else an error message.
-    const char *analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold);
+    const char *analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
+                        int smem_budget_doubles = 13500);
 };
 
 // Approximate-minimum-degree stand-in: quotient-graph minimum degree with element absorption and exact external

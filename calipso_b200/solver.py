@@ -175,6 +175,12 @@ class BatchKKT:
     def synchronize(self):
         self.b.check(self.lib.cb200_synchronize(self.h))
 
+    def profile(self, reset=True):
+        """Cycle counters of the device phases, summed over the batch (diagnostic)."""
+        out = np.zeros((self.batch, _lib.PROF_COUNT), dtype=np.int64)
+        self.b.check(self.lib.cb200_get_profile(self.h, out.ctypes.data_as(_lib.c_llp), int(reset)))
+        return {k: int(out[:, i].sum()) for i, k in enumerate(_lib.PROFILE)}
+
     def set_options(self, options: Options):
         self.options = options
         self.b.check(self.lib.cb200_set_options(self.h, C.byref(options.to_c())))

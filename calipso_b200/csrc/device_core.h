@@ -66,6 +66,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const FwdEntry *fwd;                       // (non-leaf descendants)
     const int *lcsr_ptr, *lcsr_col, *leaf_csr_pos;   // row-ordered copy of the singleton-leaf columns
     long long lcsr_total;
+    const int *leaf_e_off, *leaf_e_col, *leaf_e_pos;   // flat below-diagonal entries of the singleton leaves
     const int *big_index;                      // [ns] -> big[] (shared-memory path) or -1
     const BigTarget *big;
     const YChunk *ychunks;
@@ -362,6 +363,25 @@ CB_DEV void merit_gradient(const Ctx &ctx, const DevProblem &P, const Inst &I)
 }
 
 // ------------------------------------------------------------------------------------------------ KKT assembly
+// pan[dst[k]] = val[k]: four independent gathers in flight per thread (the stores cannot be reordered by the compiler
+// past the loads of the next iteration otherwise)
+CB_DEV void scatter_values(const Ctx &ctx, double *__restrict__ pan, const long long *__restrict__ dst,
+                           const double *__restrict__ val, int count)
+{
+#if CB_ON_DEVICE
+    int k = ctx.tid;
+    const int st = ctx.nthr;
+    for (; k + 3 * st < count; k += 4 * st) {
+        const long long d0 = dst[k], d1 = dst[k + st], d2 = dst[k + 2 * st], d3 = dst[k + 3 * st];
+        const double v0 = val[k], v1 = val[k + st], v2 = val[k + 2 * st], v3 = val[k + 3 * st];
+        pan[d0] = v0; pan[d1] = v1; pan[d2] = v2; pan[d3] = v3;
+    }
+    for (; k < count; k += st) pan[dst[k]] = val[k];
+#else
+    for (int k = 0; k < count; k++) pan[dst[k]] = val[k];
+#endif
+}
+
 // Writes the upper triangle of the reduced matrix K straight into the (zeroed) supernodal
 // panels.  eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.
 CB_DEVN void kkt_assemble(const Ctx &ctx, const DevProblem &P, const Inst &I)
@@ -379,9 +399,9 @@ CB_DEVN void kkt_assemble(const Ctx &ctx, const DevProblem &P, const Inst &I)
 #endif
     }
     ctx.sync();
-    PAR_FOR(k, P.nnzW) pan[P.dW[k]] = I.Wv[k];
-    PAR_FOR(k, P.nnzG) pan[P.dG[k]] = I.Gv[k];
-    PAR_FOR(k, P.nnzC) pan[P.dC[k]] = I.Cv[k];
+    scatter_values(ctx, pan, P.dW, I.Wv, P.nnzW);
+    scatter_values(ctx, pan, P.dG, I.Gv, P.nnzG);
+    scatter_values(ctx, pan, P.dC, I.Cv, P.nnzC);
     const double Jrr = rho + ep, Jyy = -ed, Jzz = -ed, Jss = ep;
     PAR_FOR(i, P.m) pan[P.dY[i]] = -1.0 / Jrr + Jyy;
     PAR_FOR(i, P.q_nn) {
@@ -427,7 +447,7 @@ CB_DEVN void matrix_assemble(const Ctx &ctx, const DevProblem &P, double *pan, c
     for (long long i = 0; i < 2 * n2; i++) pan[i] = 0.0;
 #endif
     ctx.sync();
-    PAR_FOR(k, P.nnzA) pan[P.dA[k]] = Ax[k];
+    scatter_values(ctx, pan, P.dA, Ax, P.nnzA);
     ctx.sync();
 }
 
@@ -787,7 +807,7 @@ template <class F, class G> CB_DEV void for_each_supernode(const Ctx &cta, const
     for (int pi = 0; pi < P.nphases; pi++) {
         const Phase ph = P.phases[forward ? pi : P.nphases - 1 - pi];
         if (ph.mode == 2) {
-            g(cta, ph.begin, ph.end);
+            g(cta, ph.begin, ph.end, ph.ebegin, ph.eend);
         } else if (ph.mode == 1) {
             for (int q = ph.begin; q < ph.end; q++) f(cta, P.order[q]);
         } else {
@@ -814,21 +834,44 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
                 if (!c.warp_scope) pt.stop(PROF_FACTOR_BIG_GENERIC);
             }
         },
-        [&](const Ctx &ctx, int begin, int end) {   // singleton leaves: L = a / d
+        [&](const Ctx &ctx, int begin, int end, int ebegin, int eend) {   // singleton leaves: L = a / d
             pt.stop(PROF_FACTOR_SMALL);
-            PAR_FOR(q, end - begin) {
+            PAR_FOR(q, end - begin) {       // pivots
                 const int s = P.order[begin + q], c0 = P.sn_start[s];
-                const int nrow = 1 + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
-                double *Ps = pan + P.panel_off[s];
-                const int *pos = P.leaf_csr_pos + P.rows_ptr[s];
-                const double dk = Ps[0], dinv = dk != 0.0 ? 1.0 / dk : 0.0;
-                for (int i = 1; i < nrow; i++) {
-                    const double l = Ps[i] * dinv;
-                    Ps[i] = l;
-                    Lcsr[pos[i - 1]] = l;     // row-ordered copy for the bulk forward pass
-                }
+                const double dk = pan[P.panel_off[s]];
                 D[c0] = dk;
-                Dinv[c0] = dinv;
+                Dinv[c0] = dk != 0.0 ? 1.0 / dk : 0.0;
+            }
+            ctx.sync();
+            {                               // entries, leaf by leaf => coalesced panel accesses
+                const int *__restrict__ eo = P.leaf_e_off + ebegin, *__restrict__ ec = P.leaf_e_col + ebegin,
+                                        *__restrict__ ep = P.leaf_e_pos + ebegin;
+                const int cnt = eend - ebegin;
+#if CB_ON_DEVICE
+                int e = ctx.tid;
+                const int st = ctx.nthr;
+                for (; e + 3 * st < cnt; e += 4 * st) {
+                    int o[4], pp[4];
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { o[u] = eo[e + u * st]; pp[u] = ep[e + u * st]; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = pan[o[u]] * Dinv[ec[e + u * st]];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { pan[o[u]] = v[u]; Lcsr[pp[u]] = v[u]; }
+                }
+                for (; e < cnt; e += st) {
+                    const double l = pan[eo[e]] * Dinv[ec[e]];
+                    pan[eo[e]] = l;
+                    Lcsr[ep[e]] = l;
+                }
+#else
+                for (int e = 0; e < cnt; e++) {
+                    const double l = pan[eo[e]] * Dinv[ec[e]];
+                    pan[eo[e]] = l;
+                    Lcsr[ep[e]] = l;     // row-ordered copy for the bulk forward pass
+                }
+#endif
             }
             ctx.sync();
             pt.stop(PROF_FACTOR_LEAVES);
@@ -988,7 +1031,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             }
             ctx.sync();
         },
-        [&](const Ctx &, int, int) {});
+        [&](const Ctx &, int, int, int, int) {});
     for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
@@ -1041,7 +1084,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             }
             ctx.sync();
         },
-        [&](const Ctx &ctx, int begin, int end) {
+        [&](const Ctx &ctx, int begin, int end, int, int) {
             PAR_FOR(q, end - begin) {
                 const int s = P.order[begin + q], c0 = P.sn_start[s];
                 const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];
@@ -1149,7 +1192,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
             }
             ctx.sync();
         },
-        [&](const Ctx &, int, int) {});   // singleton leaves have nothing to pull and no diagonal block
+        [&](const Ctx &, int, int, int, int) {});   // singleton leaves have nothing to pull and no diagonal block
     PAR_FOR(k, P.N) xp[k] *= Dinv[k];
     ctx.sync();
     pt.stop(PROF_SOLVE_FWD);
@@ -1196,7 +1239,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
             }
             ctx.sync();
         },
-        [&](const Ctx &ctx, int begin, int end) {
+        [&](const Ctx &ctx, int begin, int end, int, int) {
             PAR_FOR(q, end - begin) {
                 const int s = P.order[begin + q], c0 = P.sn_start[s];
                 const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];

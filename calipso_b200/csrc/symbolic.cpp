@@ -222,7 +222,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         }
     }
     // 4. fundamental supernodes (consecutive columns, parent = next column, nested structure) ...
-    const int max_width = 64;    // keeps (rows + width) x width panels inside the shared-memory budget
+    const int max_width = 48;    // keeps (rows + width) x width panels inside the shared-memory budget
     std::vector<int> fstart;
     for (int j = 0; j < n; j++) {
         bool merge = j > 0 && etree[j - 1] == j && Lnz[j - 1] == Lnz[j] + 1 && (j - fstart.back()) < max_width;
@@ -361,7 +361,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         while (j < ns && level[order[j]] == level[order[i]] && cls[order[j]] == cls[order[i]]) j++;
         int mode = cls[order[i]] == 0 ? 2 : (cls[order[i]] == 1 ? 1 : 0);
         if (mode == 0 && j - i == 1) mode = 1;  // a lone small task: let the whole CTA help anyway
-        phases.push_back(Phase{mode, i, j});
+        phases.push_back(Phase{mode, i, j, 0, 0});
         i = j;
     }
     // 6b. shared-memory staging plan for CTA-scope targets
@@ -470,6 +470,21 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                 }
             }
         }
+    }
+    // 6d. flat entry lists of the singleton-leaf phases (coalesced scaling pass of the factorisation)
+    leaf_e_off.clear(); leaf_e_col.clear(); leaf_e_pos.clear();
+    for (Phase &ph : phases) {
+        if (ph.mode != 2) continue;
+        ph.ebegin = (int)leaf_e_off.size();
+        for (int q = ph.begin; q < ph.end; q++) {
+            const int t = order[q];
+            for (int r = rows_ptr[t]; r < rows_ptr[t + 1]; r++) {
+                leaf_e_off.push_back((int)(panel_off[t] + 1 + (r - rows_ptr[t])));
+                leaf_e_col.push_back(sn_start[t]);
+                leaf_e_pos.push_back(leaf_csr_pos[r]);
+            }
+        }
+        ph.eend = (int)leaf_e_off.size();
     }
     // 7. destination of every input entry in the panel storage
     dest.assign(nnzA, 0);

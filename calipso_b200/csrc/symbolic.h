@@ -22,6 +22,7 @@ struct Phase {
     int mode;        // 0: one warp per supernode (tasks run concurrently); 1: whole CTA per supernode (sequential);
                      // 2: singleton leaves (width 1, no incoming update), one thread per supernode
     int begin, end;  // range in Symbolic::order
+    int ebegin, eend; // mode 2: range in the flat leaf-entry lists (leaf_e_off / leaf_e_col / leaf_e_pos)
 };
 
 // A CTA-scope target whose panel fits in shared memory pulls ALL its descendants' columns at once: they are staged
@@ -82,6 +83,9 @@ struct Symbolic {
     std::vector<int> lcsr_col;       // pivot column of the leaf
     std::vector<int> leaf_csr_pos;   // [rows.size()] for entry q of rows[] of a singleton leaf: its position in Lcsr (-1 else)
     long long lcsr_total = 0;
+    // flat list of the below-diagonal entries of the singleton leaves, grouped by phase, leaf by leaf: panel offset of
+    // the entry, pivot column of its leaf, position of its row-ordered copy in Lcsr
+    std::vector<int> leaf_e_off, leaf_e_col, leaf_e_pos;
     // shared-memory path for big targets
     std::vector<int> big_index;   // [ns] index into big, or -1
     std::vector<BigTarget> big;

@@ -155,8 +155,18 @@ struct Ctx {
 
 #if CB_ON_DEVICE
 #define PAR_FOR(i, count) for (int i = ctx.tid; i < (count); i += ctx.nthr)
+// The CTA's shared memory is named directly (not through the generic pointers of Ctx) so that the compiler emits
+// LDS/STS and knows that shared and global accesses cannot alias.
+extern __shared__ __align__(16) double cb_dyn_smem[];
+__shared__ double cb_red[34];
+__shared__ __align__(8) unsigned long long cb_bars[2];
+__shared__ unsigned cb_bar_uses;
+#define CB_SCRATCH(ctx) (cb_dyn_smem)
+#define CB_RED(ctx) (cb_red)
 #else
 #define PAR_FOR(i, count) for (int i = 0; i < (count); i++)
+#define CB_SCRATCH(ctx) ((ctx).scratch)
+#define CB_RED(ctx) ((ctx).red)
 #endif
 
 // Reductions over f(i), i in [0,n): every thread of the scope returns the same value.  Fixed association order
@@ -170,15 +180,15 @@ template <class F> CB_DEV double scope_sum(const Ctx &ctx, int n, F f)
     if (ctx.warp_scope) return a;
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     __syncthreads();
-    if (lane == 0) ctx.red[wid] = a;
+    if (lane == 0) CB_RED(ctx)[wid] = a;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int k = 0; k < nw; k++) t += ctx.red[k];
-        ctx.red[33] = t;
+        for (int k = 0; k < nw; k++) t += CB_RED(ctx)[k];
+        CB_RED(ctx)[33] = t;
     }
     __syncthreads();
-    a = ctx.red[33];
+    a = CB_RED(ctx)[33];
 #endif
     return a;
 }
@@ -192,15 +202,15 @@ template <class F> CB_DEV double scope_max(const Ctx &ctx, int n, F f)
     if (ctx.warp_scope) return a;
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     __syncthreads();
-    if (lane == 0) ctx.red[wid] = a;
+    if (lane == 0) CB_RED(ctx)[wid] = a;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int k = 0; k < nw; k++) t = ctx.red[k] > t ? ctx.red[k] : t;
-        ctx.red[33] = t;
+        for (int k = 0; k < nw; k++) t = CB_RED(ctx)[k] > t ? CB_RED(ctx)[k] : t;
+        CB_RED(ctx)[33] = t;
     }
     __syncthreads();
-    a = ctx.red[33];
+    a = CB_RED(ctx)[33];
 #endif
     return a;
 }
@@ -629,7 +639,7 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
     const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
     const int ldp = nrow + w, ldy = bt.ldy;
     double *Ps = pan + P.panel_off[s];
-    double *S = ctx.scratch;
+    double *S = CB_SCRATCH(ctx);
     double *Y = S + (((long long)ldp * w + 1) & ~1LL);
     pt.start();
 #if CB_ON_DEVICE
@@ -929,14 +939,14 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     pt.start();
     const int N = P.N, Npad = (N + 1) & ~1;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    double *xs = ctx.scratch;
+    double *xs = CB_SCRATCH(ctx);
     double *buf[2] = {xs + Npad, xs + Npad + P.max_sb_doubles};
-    unsigned long long *bars = ctx.bars;
+    unsigned long long *bars = cb_bars;
     double *tmpv = buf[1] + P.max_sb_doubles;
     for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
     __syncthreads();
     // the barriers live for the whole kernel: continue the issue/consume numbering where the previous solve stopped
-    unsigned issued = *ctx.bar_uses, consumed = issued;
+    unsigned issued = cb_bar_uses, consumed = issued;
     const int *seq = P.big_seq;
     auto issue = [&](int seq_idx) {    // called by all threads after a CTA barrier; thread 0 launches the copy
         if (tid == 0) {
@@ -1101,7 +1111,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
     if (tid == 0 && istat) istat[I_SOLVES]++;
     __syncthreads();
-    if (tid == 0) *ctx.bar_uses = issued;
+    if (tid == 0) cb_bar_uses = issued;
     __syncthreads();
     pt.stop(PROF_SOLVE_BWD);
 }
@@ -1149,7 +1159,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
                 const int nR = nrow - w;
                 const int *R = P.rows + P.rows_ptr[s];
                 const double *M = Tinv + bt.tinv_off, *LR = M + (long long)bt.ldm * w;
-                double *y = ctx.scratch;
+                double *y = CB_SCRATCH(ctx);
                 PAR_FOR(j, w) {
                     double acc = 0.0;
                     for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
@@ -1210,7 +1220,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
                 // x_t = M (D (Dinv y_t - LR' x_R))
                 const BigTarget bt = P.big[bi];
                 const double *M = Tinv + bt.tinv_off, *LR = M + (long long)bt.ldm * w;
-                double *dv = ctx.scratch;
+                double *dv = CB_SCRATCH(ctx);
                 PAR_FOR(k, w) {
                     double acc = 0.0;
                     const double *col = LR + (long long)k * bt.ldr;

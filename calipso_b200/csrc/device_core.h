@@ -71,6 +71,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const BigTarget *big;
     const YChunk *ychunks;
     const int *ystage_src, *ystage_dst, *ypiv;
+    const unsigned *ymask;
     long long tinv_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
     int nbig, max_sb_doubles, solve_smem;
@@ -541,84 +542,105 @@ CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, d
 }
 
 #if CB_ON_DEVICE
-// Blocked LDL' of a (rows x w) column-major panel in shared memory, CUDA-specific: NB columns at a time, one thread
-// per row keeps its NB entries in registers; the pivot row is broadcast through shared memory (double-buffered, one
-// barrier per pivot); the trailing columns get a rank-NB update with 4x4 register tiles.  Same arithmetic as
-// panel_factor (right-looking, L = A D^-1).  dd[] receives the pivots.
-template <int NB>
-__device__ __forceinline__ void panel_factor_smem(double *S, int rows, int w, int ld, double *pivbuf, double *dd)
+// FP64 tensor-core tile: C(8x8) += A(8x4) B(4x8), mma.sync m8n8k4 (SASS DMMA).  Lane l holds A[l/4][l%4], B[l%4][l/4],
+// C[l/4][2(l%4)] and C[l/4][2(l%4)+1].
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
 {
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int kb = 0; kb < w; kb += NB) {
-        const int nb = min(NB, w - kb);
-        double a[NB];
-        for (int rbase = kb; rbase < rows; rbase += nthr) {     // normally one pass (rows <= blockDim)
-            const int i = rbase + tid;
-            const bool active = i < rows;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Blocked right-looking LDL' of the (rows x w) column-major panel S in shared memory (leading dimension ld = 4 mod 8,
+// every row below `rows` up to the next multiple of 8 readable and finite).  Eight columns at a time:
+//   1. one thread per row keeps its 8 entries in registers; the warp that owns the 8 pivot rows eliminates them with
+//      shuffles (no CTA barrier inside the block) and publishes the unscaled pivot rows U and the reciprocals;
+//   2. after one barrier the other warps eliminate their rows against U, every row writes L back, the rows that are
+//      also columns of the trailing part write their unscaled multipliers L*D to LD;
+//   3. the trailing columns get their rank-8 update S -= L (L D)' on the FP64 tensor cores, one warp per 8-row strip.
+// Same arithmetic as panel_factor (L = A D^-1, zero pivot => zero column).  dd[] receives the pivots.
+__device__ __forceinline__ void panel_factor_tc(double *__restrict__ S, int rows, int w, int ld, double *__restrict__ U,
+                                                double *__restrict__ dinvs, double *__restrict__ dd,
+                                                double *__restrict__ LD, int ldw)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int i = tid;                       // this thread's row (rows <= blockDim.x)
+    for (int kb = 0; kb < w; kb += 8) {
+        const int nb = min(8, w - kb);
+        const bool active = i >= kb && i < rows;
+        double a[8], u[8];
 #pragma unroll
-            for (int cc = 0; cc < NB; cc++) a[cc] = (active && cc < nb) ? S[i + (kb + cc) * ld] : 0.0;
+        for (int c = 0; c < 8; c++) a[c] = (active && c < nb) ? S[i + (kb + c) * ld] : 0.0;
+        const int pw = kb >> 5, base = kb & 31;
+        if (warp == pw) {
 #pragma unroll
-            for (int k = 0; k < NB; k++) {
+            for (int k = 0; k < 8; k++) {
                 if (k < nb) {
-                    // broadcast column k of the diagonal block (unscaled): pb[c] = A[kb+c, kb+k], c >= k; pb[k] = pivot
-                    double *pb = pivbuf + (k & 1) * NB;
-                    if (rbase == kb && i >= kb + k && i < kb + nb) pb[i - kb] = a[k];
-                    __syncthreads();
-                    const double d = pb[k];
+                    double pr[8];
+#pragma unroll
+                    for (int cc = 0; cc < 8; cc++)
+                        if (cc >= k) pr[cc] = __shfl_sync(0xffffffffu, a[k], base + cc);   // A[kb+cc, kb+k], unscaled
+                    const double d = pr[k];
                     const double dinv = d != 0.0 ? 1.0 / d : 0.0;
+                    if (lane == 0) {
+                        dinvs[k] = dinv;
+                        dd[kb + k] = d;
+#pragma unroll
+                        for (int cc = 0; cc < 8; cc++)
+                            if (cc > k) U[k * 8 + cc] = pr[cc];
+                    }
+                    u[k] = a[k];
                     if (active && i > kb + k) {
                         const double lik = a[k] * dinv;
 #pragma unroll
-                        for (int cc = 0; cc < NB; cc++)
-                            if (cc > k) a[cc] -= lik * pb[cc];
+                        for (int cc = 0; cc < 8; cc++)
+                            if (cc > k) a[cc] -= lik * pr[cc];
                         a[k] = lik;
                     }
-                    if (rbase == kb && i == kb + k) dd[kb + k] = d;
                 }
             }
-            if (active) {
-#pragma unroll
-                for (int cc = 0; cc < NB; cc++)
-                    if (cc < nb) S[i + (kb + cc) * ld] = a[cc];
-            }
-            __syncthreads();
         }
-        // trailing update: S[i, j] -= sum_c L[i, kb+c] d_c L[j, kb+c] for j >= kb+nb, i >= j
+        __syncthreads();
+        if (warp != pw && active) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k < nb) {
+                    u[k] = a[k];
+                    const double lik = a[k] * dinvs[k];
+#pragma unroll
+                    for (int cc = 0; cc < 8; cc++)
+                        if (cc > k && cc < nb) a[cc] -= lik * U[k * 8 + cc];
+                    a[k] = lik;
+                }
+            }
+        }
         const int j0 = kb + nb;
-        if (j0 < w) {
-            const int ntJ = (w - j0 + 3) >> 2, ntI = (rows - j0 + 3) >> 2;
-            for (int tile = tid; tile < ntI * ntJ; tile += nthr) {
-                const int ti = tile % ntI, tj = tile / ntI;
-                if (ti >= tj) {
-                    const int ib = j0 + 4 * ti, jb = j0 + 4 * tj;
-                    double acc[4][4];
+        if (active) {
 #pragma unroll
-                    for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 8; c++)
+                if (c < nb && i > kb + c) S[i + (kb + c) * ld] = a[c];
+            if (j0 < w && i >= j0 && i < w) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < NB; cc++) {
-                        if (cc < nb) {
-                            const double dc = dd[kb + cc];
-                            double av[4], bv[4];
-#pragma unroll
-                            for (int r = 0; r < 4; r++) {
-                                av[r] = (ib + r < rows) ? S[ib + r + (kb + cc) * ld] : 0.0;
-                                bv[r] = (jb + r < rows) ? S[jb + r + (kb + cc) * ld] * dc : 0.0;
-                            }
-#pragma unroll
-                            for (int r = 0; r < 4; r++)
-#pragma unroll
-                                for (int q = 0; q < 4; q++) acc[r][q] += av[r] * bv[q];
-                        }
+                for (int c = 0; c < 8; c++) LD[c * ldw + i] = u[c];
+            }
+        }
+        __syncthreads();
+        if (j0 < w) {      // nb == 8 here
+            const int ntI = (rows + 7) >> 3, ntJ = (w + 7) >> 3, tj0 = j0 >> 3;
+            for (int ti = tj0 + warp; ti < ntI; ti += nwarps) {
+                const double a0 = -S[8 * ti + gid + (kb + tig) * ld], a1 = -S[8 * ti + gid + (kb + 4 + tig) * ld];
+                const int r = 8 * ti + gid;
+                const int tjmax = min(ti, ntJ - 1);
+                for (int tj = tj0; tj <= tjmax; tj++) {
+                    const double b0 = LD[tig * ldw + 8 * tj + gid], b1 = LD[(4 + tig) * ldw + 8 * tj + gid];
+                    const int col = 8 * tj + 2 * tig;
+                    double c0 = col < w ? S[r + col * ld] : 0.0, c1 = col + 1 < w ? S[r + (col + 1) * ld] : 0.0;
+                    dmma_8x8x4(c0, c1, a0, b0);
+                    dmma_8x8x4(c0, c1, a1, b1);
+                    if (r < rows) {
+                        if (col < w) S[r + col * ld] = c0;
+                        if (col + 1 < w) S[r + (col + 1) * ld] = c1;
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            const int Ii = ib + r, Jj = jb + q;
-                            if (Ii < rows && Jj < w && Ii >= Jj) S[Ii + Jj * ld] -= acc[r][q];
-                        }
                 }
             }
             __syncthreads();
@@ -628,29 +650,30 @@ __device__ __forceinline__ void panel_factor_smem(double *S, int rows, int w, in
 #endif
 
 // CTA-scope supernode on the shared-memory path.  All descendant columns that touch the target are staged as the
-// columns of a dense matrix Y (rows = target rows) and applied as ONE register-tiled GEMM  S -= Y diag(D) Y_top'
-// instead of one barrier per descendant.  The panel carries w extra rows initialised to the identity: after the
-// elimination they hold M = L_tt^-T D_t^-1, which turns the triangular solves of this supernode into mat-vecs
-// (ldl_solve).  Layout of ctx.scratch: S[(nrow+w) x w] | Y[ldy x kc] | Dy[kc].
+// columns of a dense matrix Y (rows = target rows) and applied as ONE GEMM  S -= Y diag(D) Y_top' instead of one
+// barrier per descendant: on the device on the FP64 tensor cores (mma.sync m8n8k4), 8x8 output tiles, skipping the
+// 8x4 blocks of Y that are structurally zero (P.ymask).  The panel carries w extra rows initialised to the identity:
+// after the elimination they hold M = L_tt^-T D_t^-1, which turns the triangular solves of this supernode into
+// mat-vecs (ldl_solve).  Layout of the work area: S[ldp x w] | Y[ldy x kc4] | Dy[kc4]; the Y area is reused by the
+// panel factorisation (U, reciprocals, pivots, unscaled multipliers).
 CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv,
                                  double *Tinv, int s, const BigTarget bt, ProfTimer &pt)
 {
     const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
     const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
-    const int ldp = nrow + w, ldy = bt.ldy;
+    const int ldp = bt.ldp, ldy = bt.ldy;
     double *Ps = pan + P.panel_off[s];
     double *S = CB_SCRATCH(ctx);
-    double *Y = S + (((long long)ldp * w + 1) & ~1LL);
+    double *Y = S + (long long)ldp * w;
     pt.start();
 #if CB_ON_DEVICE
-    {   // panel + identity rows, column by column (coalesced, no div/mod)
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int k = wid; k < w; k += nw) {
-            const double *src = Ps + k * nrow;
-            double *dst = S + k * ldp;
-            for (int i = lane; i < nrow; i += 32) dst[i] = src[i];
-            for (int i = lane; i < w; i += 32) dst[nrow + i] = (i == k) ? 1.0 : 0.0;
-        }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // panel + identity rows + zero padding, column by column (coalesced)
+    for (int k = wid; k < w; k += nw) {
+        const double *__restrict__ src = Ps + k * nrow;
+        double *dst = S + k * ldp;
+        for (int i = lane; i < nrow; i += 32) dst[i] = src[i];
+        for (int i = nrow + lane; i < ldp; i += 32) dst[i] = (i - nrow == k) ? 1.0 : 0.0;
     }
 #else
     PAR_FOR(e, ldp * w) {
@@ -660,36 +683,37 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
 #endif
     for (int ci = bt.chunk_begin; ci < bt.chunk_end; ci++) {
         const YChunk ch = P.ychunks[ci];
-        const int kc = ch.col_end - ch.col_begin;
-        double *Dy = Y + (long long)ldy * kc;
+        const int kc = ch.col_end - ch.col_begin, kc4 = (kc + 3) & ~3;
+        double *Dy = Y + (long long)ldy * kc4;
 #if CB_ON_DEVICE
         {
             double2 *Y2 = reinterpret_cast<double2 *>(Y);
-            const int n2 = (ldy * kc) >> 1;     // ldy is a multiple of 4
+            const int n2 = (ldy * kc4) >> 1;     // ldy is a multiple of 4
             for (int e = ctx.tid; e < n2; e += ctx.nthr) Y2[e] = make_double2(0.0, 0.0);
         }
 #else
-        PAR_FOR(e, ldy * kc) Y[e] = 0.0;
+        PAR_FOR(e, ldy * kc4) Y[e] = 0.0;
 #endif
-        PAR_FOR(cc, kc) Dy[cc] = D[P.ypiv[ch.piv_begin + cc]];
+        PAR_FOR(cc, kc4) Dy[cc] = cc < kc ? D[P.ypiv[ch.piv_begin + cc]] : 0.0;
         ctx.sync();
 #if CB_ON_DEVICE
-        {   // scatter with four loads in flight per thread
+        {   // gather with eight loads in flight per thread
             const int nst = ch.stage_end - ch.stage_begin;
-            const int *src = P.ystage_src + ch.stage_begin, *dst = P.ystage_dst + ch.stage_begin;
-            for (int e = ctx.tid; e < nst; e += 4 * ctx.nthr) {
-                int sidx[4], didx[4];
-                double v[4];
+            const int *__restrict__ src = P.ystage_src + ch.stage_begin, *__restrict__ dst = P.ystage_dst + ch.stage_begin;
+            const double *__restrict__ pang = pan;
+            for (int e = ctx.tid; e < nst; e += 8 * ctx.nthr) {
+                int sidx[8], didx[8];
+                double v[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 8; u++) {
                     const int ee = e + u * ctx.nthr;
                     sidx[u] = ee < nst ? src[ee] : -1;
                     didx[u] = ee < nst ? dst[ee] : 0;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = sidx[u] >= 0 ? pan[sidx[u]] : 0.0;
+                for (int u = 0; u < 8; u++) v[u] = sidx[u] >= 0 ? pang[sidx[u]] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < 8; u++)
                     if (sidx[u] >= 0) Y[didx[u]] = v[u];
             }
         }
@@ -698,83 +722,77 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
 #endif
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_STAGE);
-        const int ntI = ldy >> 2, ntJ = (w + 3) >> 2;
-        PAR_FOR(tile, ntI * ntJ) {
-            const int ti = tile % ntI, tj = tile / ntI;
-            if (4 * ti + 3 >= 4 * tj) {
-                double acc[4][4];
 #if CB_ON_DEVICE
-#pragma unroll
-#endif
-                for (int r = 0; r < 4; r++)
-#if CB_ON_DEVICE
-#pragma unroll
-#endif
-                    for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
-                const double *ya = Y + 4 * ti, *yb = Y + 4 * tj;
-                for (int cc = 0; cc < kc; cc++) {
-                    const double dcc = Dy[cc];
-                    double a[4], b[4];
-#if CB_ON_DEVICE
-                    const double2 a01 = *reinterpret_cast<const double2 *>(ya + cc * ldy);
-                    const double2 a23 = *reinterpret_cast<const double2 *>(ya + cc * ldy + 2);
-                    const double2 b01 = *reinterpret_cast<const double2 *>(yb + cc * ldy);
-                    const double2 b23 = *reinterpret_cast<const double2 *>(yb + cc * ldy + 2);
-                    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
-                    b[0] = b01.x * dcc; b[1] = b01.y * dcc; b[2] = b23.x * dcc; b[3] = b23.y * dcc;
-#pragma unroll
-#else
-                    for (int r = 0; r < 4; r++) { a[r] = ya[r + cc * ldy]; b[r] = yb[r + cc * ldy] * dcc; }
-#endif
-                    for (int r = 0; r < 4; r++)
-#if CB_ON_DEVICE
-#pragma unroll
-#endif
-                        for (int q = 0; q < 4; q++) acc[r][q] += a[r] * b[q];
-                }
-#if CB_ON_DEVICE
-#pragma unroll
-#endif
-                for (int q = 0; q < 4; q++)
-#if CB_ON_DEVICE
-#pragma unroll
-#endif
-                    for (int r = 0; r < 4; r++) {
-                        const int Ii = 4 * ti + r, Jj = 4 * tj + q;
-                        if (Ii < nrow && Jj < w && Ii >= Jj) S[Ii + Jj * ldp] -= acc[r][q];
+        {   // S[i, j] -= sum_c Y[i, c] Dy[c] Y[j, c] for the 8x8 tiles that touch the lower triangle
+            const int gid = lane >> 2, tig = lane & 3;
+            const int ntI = (nrow + 7) >> 3, ntJ = (w + 7) >> 3;
+            const unsigned *__restrict__ msk = P.ymask + ch.mask_begin;
+            for (int tile = wid; tile < ntI * ntJ; tile += nw) {
+                const int tj = tile / ntI, ti = tile - tj * ntI;
+                if (ti < tj) continue;
+                unsigned m = msk[ti] & msk[tj];
+                if (!m) continue;
+                const double *ya = Y + 8 * ti + gid + tig * ldy, *yb = Y + 8 * tj + gid + tig * ldy;
+                const double *dy = Dy + tig;
+                double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+                while (m) {
+                    const int g = __ffs(m) - 1;
+                    m &= m - 1;
+                    dmma_8x8x4(e0, e1, ya[4 * g * ldy], yb[4 * g * ldy] * dy[4 * g]);
+                    if (m) {
+                        const int g2 = __ffs(m) - 1;
+                        m &= m - 1;
+                        dmma_8x8x4(f0, f1, ya[4 * g2 * ldy], yb[4 * g2 * ldy] * dy[4 * g2]);
                     }
+                }
+                const int r = 8 * ti + gid, col = 8 * tj + 2 * tig;
+                if (r < nrow) {
+                    if (col < w) S[r + col * ldp] -= e0 + f0;
+                    if (col + 1 < w) S[r + (col + 1) * ldp] -= e1 + f1;
+                }
             }
         }
+#else
+        PAR_FOR(e, nrow * w) {
+            const int j = e / nrow, i = e % nrow;
+            if (i >= j) {
+                double acc = 0.0;
+                for (int cc = 0; cc < kc; cc++) acc += Y[i + (long long)cc * ldy] * (Y[j + (long long)cc * ldy] * Dy[cc]);
+                S[i + (long long)j * ldp] -= acc;
+            }
+        }
+#endif
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_GEMM);
     }
+    double *dd = Y + 72;                 // w pivots
 #if CB_ON_DEVICE
-    {
-        double *pivbuf = Y;              // 2 * NB doubles
-        double *dd = Y + 32;             // w doubles
-        __syncthreads();
-        if (ldp <= (int)blockDim.x) panel_factor_smem<8>(S, ldp, w, ldp, pivbuf, dd);
-        else panel_factor(ctx, S, ldp, w, ldp);
+    if (nrow + w <= (int)blockDim.x) {
+        const int ldw = ((w + 7) & ~7) + 4;
+        panel_factor_tc(S, nrow + w, w, ldp, Y, Y + 64, dd, Y + 72 + ((w + 3) & ~3), ldw);
+    } else {
+        panel_factor(ctx, S, nrow + w, w, ldp);
+        PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
+        ctx.sync();
     }
 #else
-    panel_factor(ctx, S, ldp, w, ldp);
+    panel_factor(ctx, S, nrow + w, w, ldp);
+    PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
+    ctx.sync();
 #endif
     // write back: factor panel, pivots, and the solve block [M | LR] with odd leading dimensions
     double *Mblk = Tinv + bt.tinv_off, *LR = Mblk + (long long)bt.ldm * w;
 #if CB_ON_DEVICE
-    {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int k = wid; k < w; k += nw) {
-            const double *src = S + k * ldp;
-            for (int i = lane; i < nrow; i += 32) Ps[i + k * nrow] = src[i];
-            for (int i = lane; i < w; i += 32) Mblk[i + k * bt.ldm] = src[nrow + i];
-            for (int i = lane; i < nR; i += 32) LR[i + k * bt.ldr] = src[w + i];
-        }
+    for (int k = wid; k < w; k += nw) {
+        const double *src = S + k * ldp;
+        for (int i = lane; i < nrow; i += 32) Ps[i + k * nrow] = i == k ? dd[k] : src[i];
+        for (int i = lane; i < w; i += 32) Mblk[i + k * bt.ldm] = src[nrow + i];
+        for (int i = lane; i < nR; i += 32) LR[i + k * bt.ldr] = src[w + i];
     }
 #else
     PAR_FOR(e, nrow * w) {
         int k = e / nrow, i = e % nrow;
-        Ps[e] = S[i + (long long)k * ldp];
+        Ps[e] = i == k ? dd[k] : S[i + (long long)k * ldp];
     }
     PAR_FOR(e, w * w) {
         int k = e / w, i = e % w;
@@ -786,7 +804,7 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
     }
 #endif
     PAR_FOR(k, w) {
-        double dk = S[k + (long long)k * ldp];
+        const double dk = dd[k];
         D[c0 + k] = dk;
         Dinv[c0 + k] = dk != 0.0 ? 1.0 / dk : 0.0;
     }

@@ -366,7 +366,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     }
     // 6b. shared-memory staging plan for CTA-scope targets
     big_index.assign(ns, -1);
-    big.clear(); ychunks.clear(); ystage_src.clear(); ystage_dst.clear(); ypiv.clear(); big_seq.clear();
+    big.clear(); ychunks.clear(); ystage_src.clear(); ystage_dst.clear(); ypiv.clear(); ymask.clear(); big_seq.clear();
     max_sb_doubles = 0;
     tinv_total = 0;
     scratch_doubles = 0;
@@ -375,56 +375,68 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         for (int q = ph.begin; q < ph.end; q++) {
             int t = order[q];
             int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
-            int ldy = (nrow + 3) & ~3;
-            long long panel_d = ((long long)(nrow + w) * w + 1) & ~1LL;   // panel + w identity rows (-> M = L^-T D^-1)
-            long long tinv_d = ((long long)w * w + 1) & ~1LL;
-            long long fixed = panel_d;
+            const int ldy = ((nrow + 7) & ~7) + 4;
+            const int ldp = ((nrow + w + 7) & ~7) + 4;                   // panel + w identity rows (-> M = L^-T D^-1)
+            const int ntI = (nrow + 7) / 8;
+            const long long fixed = (long long)ldp * w;
+            // after the GEMM the Y area is reused by the panel factorisation: 8x8 pivot block, 8 reciprocals, w pivots,
+            // 8 x (w rounded + 4) unscaled multipliers
+            const long long aux = 64 + 8 + w + 8LL * (((w + 7) & ~7) + 4) + 8;
             int ktot = 0;
             for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) ktot += sn_start[upd[u].d + 1] - sn_start[upd[u].d];
-            if (fixed + (ktot > 0 ? (long long)(ldy + 1) * 8 : 0) > smem_budget_doubles) continue;   // generic path
-            int kc_max = ktot > 0 ? (int)std::min<long long>((smem_budget_doubles - fixed) / (ldy + 1), ktot) : 0;
+            if (fixed + std::max<long long>(ktot > 0 ? (long long)(ldy + 1) * 8 : 0, aux) > smem_budget_doubles) continue;   // generic path
+            int kc_max = 0;
+            if (ktot > 0) {
+                kc_max = (int)std::min<long long>((smem_budget_doubles - fixed) / (ldy + 1), 128);
+                kc_max &= ~3;                                            // whole groups of 4 columns, <= 32 groups
+            }
             BigTarget bt;
             bt.chunk_begin = (int)ychunks.size();
             bt.ldy = ldy;
+            bt.ldp = ldp;
             bt.tinv_off = (int)tinv_total;
             bt.ldm = w | 1;
             bt.ldr = (nrow - w) | 1;
             bt.sb_doubles = (int)(((long long)(bt.ldm + bt.ldr) * w + 1) & ~1LL);
             tinv_total += bt.sb_doubles;
-            (void)tinv_d;
             int col = 0;
-            YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size()};
+            YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
+            ymask.resize(ymask.size() + ntI, 0u);
             int max_kc = 0;
+            auto close_chunk = [&]() {
+                ch.col_end = col; ch.stage_end = (int)ystage_src.size();
+                max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
+                ychunks.push_back(ch);
+            };
             for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) {
                 const UpdateEntry &ue = upd[u];
                 int cd0 = sn_start[ue.d], wd = sn_start[ue.d + 1] - cd0;
                 int nRd = rows_ptr[ue.d + 1] - rows_ptr[ue.d], nrowd = wd + nRd;
                 for (int k = 0; k < wd; k++) {
                     if (col - ch.col_begin == kc_max) {   // chunk full
-                        ch.col_end = col; ch.stage_end = (int)ystage_src.size();
-                        max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
-                        ychunks.push_back(ch);
-                        ch = YChunk{col, col, (int)ystage_src.size(), 0, (int)ypiv.size()};
+                        close_chunk();
+                        ch = YChunk{col, col, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
+                        ymask.resize(ymask.size() + ntI, 0u);
                     }
                     ypiv.push_back(cd0 + k);
                     for (int i = ue.a; i < nRd; i++) {
+                        const int lrow = rel[ue.rel + (i - ue.a)], lcol = col - ch.col_begin;
                         ystage_src.push_back((int)(panel_off[ue.d] + (wd + i) + (long long)k * nrowd));
-                        ystage_dst.push_back(rel[ue.rel + (i - ue.a)] + (col - ch.col_begin) * ldy);
+                        ystage_dst.push_back(lrow + lcol * ldy);
+                        ymask[ch.mask_begin + lrow / 8] |= 1u << (lcol / 4);
                     }
                     col++;
                 }
             }
-            if (col > ch.col_begin) {
-                ch.col_end = col; ch.stage_end = (int)ystage_src.size();
-                max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
-                ychunks.push_back(ch);
-            }
+            if (col > ch.col_begin) close_chunk();
+            else ymask.resize(ch.mask_begin);
             bt.chunk_end = (int)ychunks.size();
             big_index[t] = (int)big.size();
             big.push_back(bt);
             big_seq.push_back(t);
             max_sb_doubles = std::max(max_sb_doubles, bt.sb_doubles);
-            scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>((long long)max_kc * (ldy + 1), 40 + w) + 8);
+            const long long ysize = (long long)((max_kc + 3) & ~3) * (ldy + 1);
+            scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>(ysize, aux) + 8);
         }
     }
     big_seq_bwd.clear();

@@ -32,10 +32,14 @@ struct YChunk {
     int col_begin, col_end;      // Y columns of this chunk
     int stage_begin, stage_end;  // range in ystage_src / ystage_dst
     int piv_begin;               // ypiv[piv_begin + c]: pivot (permuted column) of chunk column c
+    int mask_begin;              // ymask[mask_begin + ti]: bit g set <=> rows [8ti, 8ti+8) x columns [4g, 4g+4) of the chunk
+                                 // hold a structural non-zero (the tensor-core GEMM skips the other 8x4 blocks)
 };
 struct BigTarget {
     int chunk_begin, chunk_end;
-    int ldy;                     // leading dimension of Y (rows padded to a multiple of 4)
+    int ldy;                     // leading dimension of Y: rows rounded up to a multiple of 8, plus 4 (=> 8x4 fragment
+                                 // loads of the FP64 mma hit 16 distinct shared-memory banks per half-warp)
+    int ldp;                     // leading dimension of the panel work area (rows + w identity rows, same rounding)
     int tinv_off;                // offset of this supernode's solve block in the Tinv storage:
                                  //   M  = L_tt^-T D_t^-1   (w x w,  leading dimension ldm, odd => bank-conflict free)
                                  //   LR = L[R_t, t]        (nR x w, leading dimension ldr, odd), at tinv_off + ldm*w
@@ -91,6 +95,7 @@ struct Symbolic {
     std::vector<BigTarget> big;
     std::vector<YChunk> ychunks;
     std::vector<int> ystage_src, ystage_dst, ypiv;
+    std::vector<unsigned> ymask;
     std::vector<int> big_seq;     // shared-memory supernodes in forward schedule order (TMA prefetch chain)
     std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
     int max_sb_doubles = 0;       // largest solve block

@@ -54,6 +54,7 @@ struct Batch {
 };
 
 #define CB_THREADS 256
+#define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
 #define CTX_SETUP                                                                                          \
     if (threadIdx.x == 0) {                                                                                \
         mbar_init(&cb_bars[0], 1);                                                                         \
@@ -69,13 +70,13 @@ struct Batch {
     if (b >= B.count) return;                             \
     Inst I = B.inst(P, b);
 
-__global__ void __launch_bounds__(CB_THREADS) k_cone(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int flags, int at_candidate)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_cone(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int flags, int at_candidate)
 {
     KERNEL_PROLOGUE
     cone_eval(ctx, P, I, at_candidate ? I.cand : I.w, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1);
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_residual(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_residual(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {
     KERNEL_PROLOGUE
     residual_eval(ctx, P, I);
@@ -83,14 +84,14 @@ __global__ void __launch_bounds__(CB_THREADS) k_residual(const __grid_constant__
     if (ctx.tid == 0) I.scal[S_THETA] = th;
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_search_direction(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_search_direction(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
 {
     KERNEL_PROLOGUE
     int st = search_direction(ctx, P, I, o);
     if (ctx.tid == 0) I.istat[I_STATUS] = st;
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_cone_search(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_cone_search(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
 {
     KERNEL_PROLOGUE
     int st = cone_search(ctx, P, I, o);
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_cone_search(const __grid_constan
     if (ctx.tid == 0 && st != ST_OK) I.istat[I_STATUS] = st;
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_apply_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_apply_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {
     KERNEL_PROLOGUE
     const int n = P.n, m = P.m, p = P.p, N = P.N;
@@ -118,25 +119,25 @@ __global__ void __launch_bounds__(CB_THREADS) k_apply_step(const __grid_constant
     (void)n;
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_jtimes(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_jtimes(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {   // tmp <- J * err  (err used as the input vector)
     KERNEL_PROLOGUE
     jacobian_times(ctx, P, I, I.err, I.tmp);
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_lq_evaluate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int flags, int at_candidate)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_evaluate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int flags, int at_candidate)
 {
     KERNEL_PROLOGUE
     lq_evaluate(ctx, P, I, at_candidate ? I.cand : I.w, flags);
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_lq_begin(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o, int warmstart)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_begin(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o, int warmstart)
 {
     KERNEL_PROLOGUE
     solve_begin_lq(ctx, P, I, o, warmstart);
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
 {
     KERNEL_PROLOGUE
     solve_step_lq(ctx, P, I, o);
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_lq_step(const __grid_constant__ 
 
 // LinearSolver seam: factor the generic matrix / solve in place.  These two are the "KKT LDL^T solve" whose HBM
 // roofline bench.py reports (B_unit).
-__global__ void __launch_bounds__(CB_THREADS) k_ldl_factor(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int assemble_generic)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_factor(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int assemble_generic)
 {
     CTX_SETUP
     const int b = blockIdx.x;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_ldl_factor(const __grid_constant
     ldl_factor(ctx, P, pan, D, Dinv, B.Tinv + b * P.tinv_total, B.Lcsr + b * P.lcsr_total, istat, B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {
     CTX_SETUP
     const int b = blockIdx.x;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_ldl_solve(const __grid_constant_
 }
 
 // KKT path: assemble + factor with the current regularisation (no inertia loop) -- used by the roofline bench
-__global__ void __launch_bounds__(CB_THREADS) k_kkt_factor_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nsolves)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nsolves)
 {
     KERNEL_PROLOGUE
     ProfTimer pt{I.prof, 0};

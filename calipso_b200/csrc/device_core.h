@@ -65,6 +65,8 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const int *fwd_ptr;                        // per permuted column: range of (descendant, row) pairs in fwd
     const FwdEntry *fwd;                       // (non-leaf descendants)
     const int *lcsr_ptr, *lcsr_col, *leaf_csr_pos;   // row-ordered copy of the singleton-leaf columns
+    const int *lcsr_cols;                            // the columns that have singleton-leaf descendants
+    int lcsr_ncols;
     long long lcsr_total;
     const int *leaf_e_off, *leaf_e_col, *leaf_e_pos;   // flat below-diagonal entries of the singleton leaves
     const int *big_index;                      // [ns] -> big[] (shared-memory path) or -1
@@ -542,6 +544,41 @@ CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, d
 }
 
 #if CB_ON_DEVICE
+// ---- asynchronous copies: TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier, and cp.async (SASS LDGSTS)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+#endif
+
+#if CB_ON_DEVICE
 // FP64 tensor-core tile: C(8x8) += A(8x4) B(4x8), mma.sync m8n8k4 (SASS DMMA).  Lane l holds A[l/4][l%4], B[l%4][l/4],
 // C[l/4][2(l%4)] and C[l/4][2(l%4)+1].
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
@@ -652,10 +689,9 @@ __device__ __forceinline__ void panel_factor_tc(double *__restrict__ S, int rows
 // CTA-scope supernode on the shared-memory path.  All descendant columns that touch the target are staged as the
 // columns of a dense matrix Y (rows = target rows) and applied as ONE GEMM  S -= Y diag(D) Y_top' instead of one
 // barrier per descendant: on the device on the FP64 tensor cores (mma.sync m8n8k4), 8x8 output tiles, skipping the
-// 8x4 blocks of Y that are structurally zero (P.ymask).  The panel carries w extra rows initialised to the identity:
-// after the elimination they hold M = L_tt^-T D_t^-1, which turns the triangular solves of this supernode into
-// mat-vecs (ldl_solve).  Layout of the work area: S[ldp x w] | Y[ldy x kc4] | Dy[kc4]; the Y area is reused by the
-// panel factorisation (U, reciprocals, pivots, unscaled multipliers).
+// 8x4 blocks of Y that are structurally zero (P.ymask).  Layout of the work area: S[ldp x w] | Y[ldy x kc4] | Dy[kc4];
+// the staging lists carry the pivots of the Y columns as extra entries (src < 0 -> D[-1 - src]); the Y area is reused
+// by the panel factorisation (U, reciprocals, pivots, unscaled multipliers).
 CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv,
                                  double *Tinv, int s, const BigTarget bt, ProfTimer &pt)
 {
@@ -665,60 +701,70 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
     double *Ps = pan + P.panel_off[s];
     double *S = CB_SCRATCH(ctx);
     double *Y = S + (long long)ldp * w;
+    (void)Tinv;
     pt.start();
 #if CB_ON_DEVICE
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    // panel + identity rows + zero padding, column by column (coalesced)
+    // the assembled panel streams into shared memory asynchronously (LDGSTS) while the first chunk is staged
     for (int k = wid; k < w; k += nw) {
-        const double *__restrict__ src = Ps + k * nrow;
+        const double *src = Ps + k * nrow;
         double *dst = S + k * ldp;
-        for (int i = lane; i < nrow; i += 32) dst[i] = src[i];
-        for (int i = nrow + lane; i < ldp; i += 32) dst[i] = (i - nrow == k) ? 1.0 : 0.0;
+        for (int i = lane; i < nrow; i += 32) cp_async8(dst + i, src + i);
+        for (int i = nrow + lane; i < ldp; i += 32) dst[i] = 0.0;
     }
+    bool panel_pending = true;
 #else
     PAR_FOR(e, ldp * w) {
         int k = e / ldp, i = e % ldp;
-        S[e] = i < nrow ? Ps[i + (long long)k * nrow] : (i - nrow == k ? 1.0 : 0.0);
+        S[e] = i < nrow ? Ps[i + (long long)k * nrow] : 0.0;
     }
 #endif
     for (int ci = bt.chunk_begin; ci < bt.chunk_end; ci++) {
         const YChunk ch = P.ychunks[ci];
         const int kc = ch.col_end - ch.col_begin, kc4 = (kc + 3) & ~3;
-        double *Dy = Y + (long long)ldy * kc4;
+        const double *Dy = Y + (long long)ldy * kc4;
+        const int nst = ch.stage_end - ch.stage_begin;
 #if CB_ON_DEVICE
         {
-            double2 *Y2 = reinterpret_cast<double2 *>(Y);
-            const int n2 = (ldy * kc4) >> 1;     // ldy is a multiple of 4
-            for (int e = ctx.tid; e < n2; e += ctx.nthr) Y2[e] = make_double2(0.0, 0.0);
-        }
-#else
-        PAR_FOR(e, ldy * kc4) Y[e] = 0.0;
-#endif
-        PAR_FOR(cc, kc4) Dy[cc] = cc < kc ? D[P.ypiv[ch.piv_begin + cc]] : 0.0;
-        ctx.sync();
-#if CB_ON_DEVICE
-        {   // gather with eight loads in flight per thread
-            const int nst = ch.stage_end - ch.stage_begin;
             const int *__restrict__ src = P.ystage_src + ch.stage_begin, *__restrict__ dst = P.ystage_dst + ch.stage_begin;
-            const double *__restrict__ pang = pan;
-            for (int e = ctx.tid; e < nst; e += 8 * ctx.nthr) {
-                int sidx[8], didx[8];
+            const double *__restrict__ pang = pan, *__restrict__ Dg = D;
+            int sidx[8], didx[8];
+            const int nthr = ctx.nthr;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {     // indices of the first batch are in flight while Y is cleared
+                const int ee = ctx.tid + u * nthr;
+                sidx[u] = ee < nst ? src[ee] : 0x7fffffff;
+                didx[u] = ee < nst ? dst[ee] : 0;
+            }
+            double2 *Y2 = reinterpret_cast<double2 *>(Y);
+            const int n2 = ((ldy + 1) * kc4) >> 1;     // Y and Dy; kc4 is a multiple of 4
+            for (int e = ctx.tid; e < n2; e += nthr) Y2[e] = make_double2(0.0, 0.0);
+            __syncthreads();
+            for (int e = ctx.tid;;) {
                 double v[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int ee = e + u * ctx.nthr;
-                    sidx[u] = ee < nst ? src[ee] : -1;
-                    didx[u] = ee < nst ? dst[ee] : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = sidx[u] >= 0 ? pang[sidx[u]] : 0.0;
+                for (int u = 0; u < 8; u++)
+                    v[u] = sidx[u] == 0x7fffffff ? 0.0 : (sidx[u] >= 0 ? pang[sidx[u]] : Dg[-1 - sidx[u]]);
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (sidx[u] >= 0) Y[didx[u]] = v[u];
+                    if (sidx[u] != 0x7fffffff) Y[didx[u]] = v[u];
+                e += 8 * nthr;
+                if (e >= nst) break;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int ee = e + u * nthr;
+                    sidx[u] = ee < nst ? src[ee] : 0x7fffffff;
+                    didx[u] = ee < nst ? dst[ee] : 0;
+                }
             }
+            if (panel_pending) { cp_async_wait_all(); panel_pending = false; }
         }
 #else
-        PAR_FOR(e, ch.stage_end - ch.stage_begin) Y[P.ystage_dst[ch.stage_begin + e]] = pan[P.ystage_src[ch.stage_begin + e]];
+        PAR_FOR(e, (ldy + 1) * kc4) Y[e] = 0.0;
+        PAR_FOR(e, nst) {
+            const int sidx = P.ystage_src[ch.stage_begin + e];
+            Y[P.ystage_dst[ch.stage_begin + e]] = sidx >= 0 ? pan[sidx] : D[-1 - sidx];
+        }
 #endif
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_STAGE);
@@ -727,29 +773,35 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
             const int gid = lane >> 2, tig = lane & 3;
             const int ntI = (nrow + 7) >> 3, ntJ = (w + 7) >> 3;
             const unsigned *__restrict__ msk = P.ymask + ch.mask_begin;
-            for (int tile = wid; tile < ntI * ntJ; tile += nw) {
-                const int tj = tile / ntI, ti = tile - tj * ntI;
-                if (ti < tj) continue;
-                unsigned m = msk[ti] & msk[tj];
-                if (!m) continue;
-                const double *ya = Y + 8 * ti + gid + tig * ldy, *yb = Y + 8 * tj + gid + tig * ldy;
-                const double *dy = Dy + tig;
-                double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-                while (m) {
-                    const int g = __ffs(m) - 1;
-                    m &= m - 1;
-                    dmma_8x8x4(e0, e1, ya[4 * g * ldy], yb[4 * g * ldy] * dy[4 * g]);
-                    if (m) {
-                        const int g2 = __ffs(m) - 1;
+            const bool wide = ntI > 32;                                // (then the masks are read from memory per tile)
+            const unsigned mymask = lane < ntI ? msk[lane] : 0u;
+            int ti = wid, tj = 0;                                      // tiles in column-major order, warp-strided
+            while (ti >= ntI) { ti -= ntI; tj++; }
+            while (tj < ntJ) {
+                unsigned m = wide ? (msk[ti] & msk[tj])
+                                  : (__shfl_sync(0xffffffffu, mymask, ti) & __shfl_sync(0xffffffffu, mymask, tj));
+                if (ti >= tj && m) {
+                    const double *ya = Y + 8 * ti + gid + tig * ldy, *yb = Y + 8 * tj + gid + tig * ldy;
+                    const double *dy = Dy + tig;
+                    double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+                    while (m) {
+                        const int g = __ffs(m) - 1;
                         m &= m - 1;
-                        dmma_8x8x4(f0, f1, ya[4 * g2 * ldy], yb[4 * g2 * ldy] * dy[4 * g2]);
+                        dmma_8x8x4(e0, e1, ya[4 * g * ldy], yb[4 * g * ldy] * dy[4 * g]);
+                        if (m) {
+                            const int g2 = __ffs(m) - 1;
+                            m &= m - 1;
+                            dmma_8x8x4(f0, f1, ya[4 * g2 * ldy], yb[4 * g2 * ldy] * dy[4 * g2]);
+                        }
+                    }
+                    const int r = 8 * ti + gid, col = 8 * tj + 2 * tig;
+                    if (r < nrow) {
+                        if (col < w) S[r + col * ldp] -= e0 + f0;
+                        if (col + 1 < w) S[r + (col + 1) * ldp] -= e1 + f1;
                     }
                 }
-                const int r = 8 * ti + gid, col = 8 * tj + 2 * tig;
-                if (r < nrow) {
-                    if (col < w) S[r + col * ldp] -= e0 + f0;
-                    if (col + 1 < w) S[r + (col + 1) * ldp] -= e1 + f1;
-                }
+                ti += nw;
+                while (ti >= ntI) { ti -= ntI; tj++; }
             }
         }
 #else
@@ -765,42 +817,31 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_GEMM);
     }
+#if CB_ON_DEVICE
+    if (panel_pending) { cp_async_wait_all(); __syncthreads(); }
+#endif
     double *dd = Y + 72;                 // w pivots
 #if CB_ON_DEVICE
-    if (nrow + w <= (int)blockDim.x) {
+    if (nrow <= (int)blockDim.x) {
         const int ldw = ((w + 7) & ~7) + 4;
-        panel_factor_tc(S, nrow + w, w, ldp, Y, Y + 64, dd, Y + 72 + ((w + 3) & ~3), ldw);
+        panel_factor_tc(S, nrow, w, ldp, Y, Y + 64, dd, Y + 72 + ((w + 3) & ~3), ldw);
     } else {
-        panel_factor(ctx, S, nrow + w, w, ldp);
+        panel_factor(ctx, S, nrow, w, ldp);
         PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
         ctx.sync();
     }
-#else
-    panel_factor(ctx, S, nrow + w, w, ldp);
-    PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
-    ctx.sync();
-#endif
-    // write back: factor panel, pivots, and the solve block [M | LR] with odd leading dimensions
-    double *Mblk = Tinv + bt.tinv_off, *LR = Mblk + (long long)bt.ldm * w;
-#if CB_ON_DEVICE
+    // write back the factor panel (pivots on the diagonal)
     for (int k = wid; k < w; k += nw) {
         const double *src = S + k * ldp;
         for (int i = lane; i < nrow; i += 32) Ps[i + k * nrow] = i == k ? dd[k] : src[i];
-        for (int i = lane; i < w; i += 32) Mblk[i + k * bt.ldm] = src[nrow + i];
-        for (int i = lane; i < nR; i += 32) LR[i + k * bt.ldr] = src[w + i];
     }
 #else
+    panel_factor(ctx, S, nrow, w, ldp);
+    PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
+    ctx.sync();
     PAR_FOR(e, nrow * w) {
         int k = e / nrow, i = e % nrow;
         Ps[e] = i == k ? dd[k] : S[i + (long long)k * ldp];
-    }
-    PAR_FOR(e, w * w) {
-        int k = e / w, i = e % w;
-        Mblk[i + (long long)k * bt.ldm] = S[nrow + i + (long long)k * ldp];
-    }
-    PAR_FOR(e, nR * w) {
-        int k = e / nR, i = e % nR;
-        LR[i + (long long)k * bt.ldr] = S[w + i + (long long)k * ldp];
     }
 #endif
     PAR_FOR(k, w) {
@@ -917,63 +958,39 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
     pt.stop(PROF_INERTIA);
 }
 
-#if CB_ON_DEVICE
-// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-#endif
 
 #if CB_ON_DEVICE
-// Fast path of ldl_solve (same arithmetic): the permuted vector lives in shared memory for the whole solve and the
-// chain of shared-memory supernodes streams its solve blocks [M | LR] through two shared-memory buffers filled by
-// TMA bulk copies one stage ahead (mbarrier complete_tx), so no global-memory latency sits on the critical path of
-// the elimination-tree chain.  Work area: xs[N] | buf0 | buf1 | 2 mbarriers | tmp[w].
-__device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P, const double *pan, const double *D,
-                                            const double *Dinv, const double *Tinv, const double *Lcsr,
-                                            const double *b, double *x, int *istat, long long *prof)
+// Fast path of ldl_solve (same arithmetic).  The permuted vector lives in global memory (xp: 8N bytes, L1/L2
+// resident); the chain of shared-memory supernodes streams its factor panels through two shared-memory buffers filled
+// by TMA bulk copies one supernode ahead (mbarrier complete_tx), so no global-memory latency sits on the critical
+// path of the elimination-tree chain.  Per chain supernode: the w x w unit-triangular block is solved by ONE warp with
+// register-resident unknowns and shuffles (no CTA barrier per pivot), the rectangular part L_R is a mat-vec spread
+// over the whole CTA (four threads per row / column, shuffle-reduced).  Singleton leaves are handled in bulk by
+// eight-lane groups (coalesced).  Work area: buf0 | buf1 | y[64].
+__device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P, const double *__restrict__ pan,
+                                            const double *D, const double *__restrict__ Dinv,
+                                            const double *__restrict__ Lcsr, const double *b, double *x, double *xp,
+                                            int *istat, long long *prof)
 {
     ProfTimer pt{prof, 0};
     pt.start();
-    const int N = P.N, Npad = (N + 1) & ~1;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    double *xs = CB_SCRATCH(ctx);
-    double *buf[2] = {xs + Npad, xs + Npad + P.max_sb_doubles};
+    const int N = P.N;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    double *buf[2] = {cb_dyn_smem, cb_dyn_smem + P.max_sb_doubles};
+    double *yv = buf[1] + P.max_sb_doubles;
     unsigned long long *bars = cb_bars;
-    double *tmpv = buf[1] + P.max_sb_doubles;
-    for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
-    __syncthreads();
+    for (int k = tid; k < N; k += nthr) xp[k] = b[P.perm[k]];
     // the barriers live for the whole kernel: continue the issue/consume numbering where the previous solve stopped
     unsigned issued = cb_bar_uses, consumed = issued;
     const int *seq = P.big_seq;
     auto issue = [&](int seq_idx) {    // called by all threads after a CTA barrier; thread 0 launches the copy
         if (tid == 0) {
-            const BigTarget bt = P.big[P.big_index[seq[seq_idx]]];
-            const unsigned bytes = (unsigned)bt.sb_doubles * 8u;
+            const int sn = seq[seq_idx];
+            const unsigned bytes = (unsigned)P.big[P.big_index[sn]].panel_doubles * 8u;
             const int slot = issued & 1;
             fence_proxy_async();
             mbar_expect_tx(&bars[slot], bytes);
-            tma_bulk_g2s(buf[slot], Tinv + bt.tinv_off, bytes, &bars[slot]);
+            tma_bulk_g2s(buf[slot], pan + P.panel_off[sn], bytes, &bars[slot]);
         }
         issued++;
     };
@@ -983,19 +1000,24 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
         consumed++;
         return buf[slot];
     };
+    __syncthreads();
     if (P.nbig > 0) issue(0);
-    // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final)
-    for (int cidx = tid; cidx < N; cidx += nthr) {
-        const int q0 = P.lcsr_ptr[cidx], q1 = P.lcsr_ptr[cidx + 1];
-        if (q1 > q0) {
-            double a0 = 0.0, a1 = 0.0;
-            int q = q0;
-            for (; q + 1 < q1; q += 2) {
-                a0 += Lcsr[q] * xs[P.lcsr_col[q]];
-                a1 += Lcsr[q + 1] * xs[P.lcsr_col[q + 1]];
+    // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final);
+    // eight lanes per column, columns without leaf descendants are not visited
+    {
+        const int sub = tid & 7, grp = tid >> 3, ngrp = nthr >> 3;
+        for (int ci = grp; ci < P.lcsr_ncols + ((-P.lcsr_ncols) & (ngrp - 1)); ci += ngrp) {   // whole warps stay together
+            double acc = 0.0;
+            int cidx = -1;
+            if (ci < P.lcsr_ncols) {
+                cidx = P.lcsr_cols[ci];
+                const int q0 = P.lcsr_ptr[cidx], q1 = P.lcsr_ptr[cidx + 1];
+                for (int q = q0 + sub; q < q1; q += 8) acc += Lcsr[q] * xp[P.lcsr_col[q]];
             }
-            if (q < q1) a0 += Lcsr[q] * xs[P.lcsr_col[q]];
-            xs[cidx] -= a0 + a1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (sub == 0 && cidx >= 0) xp[cidx] -= acc;
         }
     }
     __syncthreads();
@@ -1007,60 +1029,72 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
             const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
             const int bi = c.warp_scope ? -1 : P.big_index[s];
-            PAR_FOR(j, w) {   // pull from small (non-leaf, non-shared-memory) descendants
-                double acc = 0.0;
-                for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
-                    const FwdEntry fe = P.fwd[q];
-                    const double *Ld = pan + fe.off;
-                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
-                }
-                if (acc != 0.0) xs[c0 + j] -= acc;
-            }
             if (bi >= 0) {
-                const BigTarget bt = P.big[bi];
-                const int *R = P.rows + P.rows_ptr[s];
+                if (tid < w) {   // pull from small (non-leaf, non-shared-memory) descendants
+                    double acc = 0.0;
+                    for (int q = P.fwd_ptr[c0 + tid]; q < P.fwd_ptr[c0 + tid + 1]; q++) {
+                        const FwdEntry fe = P.fwd[q];
+                        const double *Ld = pan + fe.off;
+                        for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
+                    }
+                    yv[tid] = xp[c0 + tid] - acc;
+                }
                 if (pos + 1 < P.nbig) issue(pos + 1);
-                const double *M = acquire(), *LR = M + bt.ldm * w;
+                const double *L = acquire();
                 pos++;
                 __syncthreads();
-                if (tid < w) {      // y_k = D_k sum_{i<=k} M[i,k] v_i
-                    const double *col = M + tid * bt.ldm;
-                    double a0 = 0.0, a1 = 0.0;
-                    int i = 0;
-                    for (; i + 1 <= tid; i += 2) { a0 += col[i] * xs[c0 + i]; a1 += col[i + 1] * xs[c0 + i + 1]; }
-                    if (i <= tid) a0 += col[i] * xs[c0 + i];
-                    tmpv[tid] = (a0 + a1) * D[c0 + tid];
+                if (wid == 0) {      // L_tt y = v, unit lower triangular, unknowns in registers (w <= 64)
+                    double y0 = lane < w ? yv[lane] : 0.0, y1 = lane + 32 < w ? yv[lane + 32] : 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < w - 1; k++) {
+                        const double l0 = (lane > k && lane < w) ? L[lane + k * nrow] : 0.0;
+                        const double l1 = (lane + 32 > k && lane + 32 < w) ? L[lane + 32 + k * nrow] : 0.0;
+                        const double yk = __shfl_sync(0xffffffffu, k < 32 ? y0 : y1, k & 31);
+                        y0 -= l0 * yk;
+                        y1 -= l1 * yk;
+                    }
+                    if (lane < w) { yv[lane] = y0; xp[c0 + lane] = y0; }
+                    if (lane + 32 < w) { yv[lane + 32] = y1; xp[c0 + lane + 32] = y1; }
                 }
                 __syncthreads();
-                if (tid < w) xs[c0 + tid] = tmpv[tid];
-                if (tid >= 64 && tid - 64 < nR) {   // push x[R] -= LR y  (a different warp set than the copy above)
-                    const int i = tid - 64;
-                    double a0 = 0.0, a1 = 0.0;
-                    int k = 0;
-                    for (; k + 1 < w; k += 2) { a0 += LR[i + k * bt.ldr] * tmpv[k]; a1 += LR[i + (k + 1) * bt.ldr] * tmpv[k + 1]; }
-                    if (k < w) a0 += LR[i + k * bt.ldr] * tmpv[k];
-                    xs[R[i]] -= a0 + a1;
-                }
-                if ((int)blockDim.x - 64 < nR) {    // more rows than spare threads: finish with a strided loop
-                    for (int i = (int)blockDim.x - 64 + tid; i < nR; i += nthr) {
-                        double a0 = 0.0;
-                        for (int k = 0; k < w; k++) a0 += LR[i + k * bt.ldr] * tmpv[k];
-                        xs[R[i]] -= a0;
+                {   // push x[R] -= L_R y, four threads per row
+                    const int *__restrict__ R = P.rows + P.rows_ptr[s];
+                    const int part = tid & 3;
+                    for (int base = 0; base < nR; base += nthr >> 2) {
+                        const int i = base + (tid >> 2);
+                        double acc = 0.0;
+                        if (i < nR) {
+                            const double *Lr = L + w + i;
+#pragma unroll 4
+                            for (int k = part; k < w; k += 4) acc += Lr[k * nrow] * yv[k];
+                        }
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                        if (part == 0 && i < nR) xp[R[i]] -= acc;
                     }
                 }
                 __syncthreads();
                 return;
             }
+            PAR_FOR(j, w) {   // pull from small (non-leaf, non-shared-memory) descendants
+                double acc = 0.0;
+                for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
+                    const FwdEntry fe = P.fwd[q];
+                    const double *Ld = pan + fe.off;
+                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
+                }
+                if (acc != 0.0) xp[c0 + j] -= acc;
+            }
             const double *Ps = pan + P.panel_off[s];
             for (int k = 0; k + 1 < w; k++) {
                 ctx.sync();
-                const double xk = xs[c0 + k];
-                PAR_FOR(i, w - 1 - k) xs[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
+                const double xk = xp[c0 + k];
+                PAR_FOR(i, w - 1 - k) xp[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
             }
             ctx.sync();
         },
         [&](const Ctx &, int, int, int, int) {});
-    for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
+    for (int k = tid; k < N; k += nthr) xp[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
     pos = 0;
@@ -1072,61 +1106,80 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             const Ctx &ctx = c;
             const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
             const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
-            const double *Ps = pan + P.panel_off[s];
-            const int *R = P.rows + P.rows_ptr[s];
+            const int *__restrict__ R = P.rows + P.rows_ptr[s];
             const int bi = c.warp_scope ? -1 : P.big_index[s];
             if (bi >= 0) {
-                const BigTarget bt = P.big[bi];
                 if (pos + 1 < P.nbig) issue(pos + 1);
-                const double *M = acquire(), *LR = M + bt.ldm * w;
+                const double *L = acquire();
                 pos++;
-                if (tid < w) {      // dv_k = D_k (x_k - sum_i LR[i,k] x[R_i])
-                    const double *col = LR + tid * bt.ldr;
-                    double a0 = 0.0, a1 = 0.0;
-                    int i = 0;
-                    for (; i + 1 < nR; i += 2) { a0 += col[i] * xs[R[i]]; a1 += col[i + 1] * xs[R[i + 1]]; }
-                    if (i < nR) a0 += col[i] * xs[R[i]];
-                    tmpv[tid] = (xs[c0 + tid] - (a0 + a1)) * D[c0 + tid];
+                {   // v_k = x_k - sum_i L_R[i, k] x[R_i], four threads per column
+                    const int part = tid & 3;
+                    for (int base = 0; base < w; base += nthr >> 2) {
+                        const int k = base + (tid >> 2);
+                        double acc = 0.0;
+                        if (k < w) {
+                            const double *Lc = L + w + k * nrow;
+#pragma unroll 4
+                            for (int i = part; i < nR; i += 4) acc += Lc[i] * xp[R[i]];
+                        }
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                        if (part == 0 && k < w) yv[k] = xp[c0 + k] - acc;
+                    }
                 }
                 __syncthreads();
-                if (tid < w) {      // x_i = sum_{k>=i} M[i,k] dv_k
-                    double a0 = 0.0, a1 = 0.0;
-                    int k = tid;
-                    for (; k + 1 < w; k += 2) { a0 += M[tid + k * bt.ldm] * tmpv[k]; a1 += M[tid + (k + 1) * bt.ldm] * tmpv[k + 1]; }
-                    if (k < w) a0 += M[tid + k * bt.ldm] * tmpv[k];
-                    xs[c0 + tid] = a0 + a1;
+                if (wid == 0) {      // L_tt' z = v, unit upper triangular
+                    double z0 = lane < w ? yv[lane] : 0.0, z1 = lane + 32 < w ? yv[lane + 32] : 0.0;
+#pragma unroll 4
+                    for (int k = w - 1; k > 0; k--) {
+                        const double l0 = lane < k ? L[k + lane * nrow] : 0.0;
+                        const double l1 = lane + 32 < k ? L[k + (lane + 32) * nrow] : 0.0;
+                        const double zk = __shfl_sync(0xffffffffu, k < 32 ? z0 : z1, k & 31);
+                        z0 -= l0 * zk;
+                        z1 -= l1 * zk;
+                    }
+                    if (lane < w) xp[c0 + lane] = z0;
+                    if (lane + 32 < w) xp[c0 + lane + 32] = z1;
                 }
                 __syncthreads();
                 return;
             }
+            const double *Ps = pan + P.panel_off[s];
             PAR_FOR(k, w) {
                 double acc = 0.0;
                 const double *col = Ps + (long long)k * nrow + w;
-                for (int i = 0; i < nR; i++) acc += col[i] * xs[R[i]];
-                xs[c0 + k] -= acc;
+                for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
+                xp[c0 + k] -= acc;
             }
             for (int k = w - 1; k > 0; k--) {
                 ctx.sync();
-                const double xk = xs[c0 + k];
-                PAR_FOR(i, k) xs[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
+                const double xk = xp[c0 + k];
+                PAR_FOR(i, k) xp[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
             }
             ctx.sync();
         },
-        [&](const Ctx &ctx, int begin, int end, int, int) {
-            PAR_FOR(q, end - begin) {
-                const int s = P.order[begin + q], c0 = P.sn_start[s];
-                const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];
-                const double *col = pan + P.panel_off[s] + 1;
-                const int *R = P.rows + P.rows_ptr[s];
-                double a0 = 0.0, a1 = 0.0;
-                int i = 0;
-                for (; i + 1 < nR; i += 2) { a0 += col[i] * xs[R[i]]; a1 += col[i + 1] * xs[R[i + 1]]; }
-                if (i < nR) a0 += col[i] * xs[R[i]];
-                xs[c0] -= a0 + a1;
+        [&](const Ctx &, int begin, int end, int, int) {   // singleton leaves: eight lanes per leaf
+            const int sub = tid & 7, grp = tid >> 3, ngrp = nthr >> 3;
+            const int cnt = end - begin;
+            for (int q = grp; q < cnt + ((-cnt) & (ngrp - 1)); q += ngrp) {
+                double acc = 0.0;
+                int c0 = -1;
+                if (q < cnt) {
+                    const int s = P.order[begin + q];
+                    c0 = P.sn_start[s];
+                    const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];
+                    const double *col = pan + P.panel_off[s] + 1;
+                    const int *__restrict__ R = P.rows + P.rows_ptr[s];
+                    for (int i = sub; i < nR; i += 8) acc += col[i] * xp[R[i]];
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (sub == 0 && c0 >= 0) xp[c0] -= acc;
             }
-            ctx.sync();
+            __syncthreads();
         });
-    for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
+    for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xp[k];
     if (tid == 0 && istat) istat[I_SOLVES]++;
     __syncthreads();
     if (tid == 0) cb_bar_uses = issued;
@@ -1144,7 +1197,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
 {
 #if CB_ON_DEVICE
     if (P.solve_smem && ctx.scratch && blockDim.x >= 128) {
-        ldl_solve_smem(ctx, P, pan, D, Dinv, Tinv, Lcsr, b, x, istat, prof);
+        ldl_solve_smem(ctx, P, pan, D, Dinv, Lcsr, b, x, xp, istat, prof);
         return;
     }
 #endif
@@ -1170,40 +1223,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
             const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
             const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
             const double *Ps = pan + P.panel_off[s];
-            const int bi = (c.warp_scope || !P.big_index || !c.scratch) ? -1 : P.big_index[s];
-            if (bi >= 0) {
-                // shared-memory supernode: pull from small descendants, y = D M' v, then PUSH  x[R] -= LR y
-                const BigTarget bt = P.big[bi];
-                const int nR = nrow - w;
-                const int *R = P.rows + P.rows_ptr[s];
-                const double *M = Tinv + bt.tinv_off, *LR = M + (long long)bt.ldm * w;
-                double *y = CB_SCRATCH(ctx);
-                PAR_FOR(j, w) {
-                    double acc = 0.0;
-                    for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
-                        const FwdEntry fe = P.fwd[q];
-                        const double *Ld = pan + fe.off;
-                        for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
-                    }
-                    xp[c0 + j] -= acc;
-                }
-                ctx.sync();
-                PAR_FOR(k, w) {
-                    double acc = 0.0;
-                    const double *col = M + (long long)k * bt.ldm;
-                    for (int i = 0; i <= k; i++) acc += col[i] * xp[c0 + i];
-                    y[k] = acc * D[c0 + k];
-                }
-                ctx.sync();
-                PAR_FOR(k, w) xp[c0 + k] = y[k];
-                PAR_FOR(i, nR) {
-                    double acc = 0.0;
-                    for (int k = 0; k < w; k++) acc += LR[i + (long long)k * bt.ldr] * y[k];
-                    xp[R[i]] -= acc;
-                }
-                ctx.sync();
-                return;
-            }
+            const int bi = P.big_index ? P.big_index[s] : -1;
             PAR_FOR(j, w) {
                 double acc = 0.0;
                 for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
@@ -1219,6 +1239,16 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
                 PAR_FOR(i, w - 1 - k) xp[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
             }
             ctx.sync();
+            if (bi >= 0) {      // shared-memory supernodes are not in the pull lists of their ancestors: PUSH x[R] -= L_R y
+                const int nR = nrow - w;
+                const int *R = P.rows + P.rows_ptr[s];
+                PAR_FOR(i, nR) {
+                    double acc = 0.0;
+                    for (int k = 0; k < w; k++) acc += Ps[(w + i) + (long long)k * nrow] * xp[c0 + k];
+                    xp[R[i]] -= acc;
+                }
+                ctx.sync();
+            }
         },
         [&](const Ctx &, int, int, int, int) {});   // singleton leaves have nothing to pull and no diagonal block
     PAR_FOR(k, P.N) xp[k] *= Dinv[k];
@@ -1233,27 +1263,6 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
             const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
             const double *Ps = pan + P.panel_off[s];
             const int *R = P.rows + P.rows_ptr[s];
-            const int bi = (c.warp_scope || !P.big_index || !c.scratch) ? -1 : P.big_index[s];
-            if (bi >= 0) {
-                // x_t = M (D (Dinv y_t - LR' x_R))
-                const BigTarget bt = P.big[bi];
-                const double *M = Tinv + bt.tinv_off, *LR = M + (long long)bt.ldm * w;
-                double *dv = CB_SCRATCH(ctx);
-                PAR_FOR(k, w) {
-                    double acc = 0.0;
-                    const double *col = LR + (long long)k * bt.ldr;
-                    for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
-                    dv[k] = (xp[c0 + k] - acc) * D[c0 + k];
-                }
-                ctx.sync();
-                PAR_FOR(i, w) {
-                    double acc = 0.0;
-                    for (int k = i; k < w; k++) acc += M[i + (long long)k * bt.ldm] * dv[k];
-                    xp[c0 + i] = acc;
-                }
-                ctx.sync();
-                return;
-            }
             PAR_FOR(k, w) {
                 double acc = 0.0;
                 const double *col = Ps + (long long)k * nrow + w;

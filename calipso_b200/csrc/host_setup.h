@@ -159,6 +159,7 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.solve_smem = S.solve_smem;
     P.lcsr_ptr = up(S.lcsr_ptr); P.lcsr_col = up(S.lcsr_col); P.leaf_csr_pos = up(S.leaf_csr_pos);
     P.lcsr_total = S.lcsr_total;
+    P.lcsr_cols = up(S.lcsr_cols); P.lcsr_ncols = (int)S.lcsr_cols.size();
     P.leaf_e_off = up(S.leaf_e_off); P.leaf_e_col = up(S.leaf_e_col); P.leaf_e_pos = up(S.leaf_e_pos);
 }
 

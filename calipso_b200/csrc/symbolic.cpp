@@ -376,7 +376,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             int t = order[q];
             int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
             const int ldy = ((nrow + 7) & ~7) + 4;
-            const int ldp = ((nrow + w + 7) & ~7) + 4;                   // panel + w identity rows (-> M = L^-T D^-1)
+            const int ldp = ((nrow + 7) & ~7) + 4;
             const int ntI = (nrow + 7) / 8;
             const long long fixed = (long long)ldp * w;
             // after the GEMM the Y area is reused by the panel factorisation: 8x8 pivot block, 8 reciprocals, w pivots,
@@ -394,16 +394,17 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             bt.chunk_begin = (int)ychunks.size();
             bt.ldy = ldy;
             bt.ldp = ldp;
-            bt.tinv_off = (int)tinv_total;
-            bt.ldm = w | 1;
-            bt.ldr = (nrow - w) | 1;
-            bt.sb_doubles = (int)(((long long)(bt.ldm + bt.ldr) * w + 1) & ~1LL);
-            tinv_total += bt.sb_doubles;
+            bt.panel_doubles = (int)(panel_off[t + 1] - panel_off[t]);
             int col = 0;
             YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
             ymask.resize(ymask.size() + ntI, 0u);
             int max_kc = 0;
             auto close_chunk = [&]() {
+                const int kc4 = (col - ch.col_begin + 3) & ~3;
+                for (int cc = 0; cc < col - ch.col_begin; cc++) {      // pivots of the Y columns: Dy[cc] = D[ypiv]
+                    ystage_src.push_back(-1 - ypiv[ch.piv_begin + cc]);
+                    ystage_dst.push_back(ldy * kc4 + cc);
+                }
                 ch.col_end = col; ch.stage_end = (int)ystage_src.size();
                 max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
                 ychunks.push_back(ch);
@@ -434,7 +435,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             big_index[t] = (int)big.size();
             big.push_back(bt);
             big_seq.push_back(t);
-            max_sb_doubles = std::max(max_sb_doubles, bt.sb_doubles);
+            max_sb_doubles = std::max(max_sb_doubles, bt.panel_doubles);
             const long long ysize = (long long)((max_kc + 3) & ~3) * (ldy + 1);
             scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>(ysize, aux) + 8);
         }
@@ -444,8 +445,8 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         if (phases[pi].mode == 1)
             for (int q = phases[pi].begin; q < phases[pi].end; q++)
                 if (big_index[order[q]] >= 0) big_seq_bwd.push_back(order[q]);
-    {   // shared-memory solve: x (N padded to even) + two solve-block buffers + barriers
-        long long need = ((long long)N + 1) / 2 * 2 + 2LL * max_sb_doubles + 16 + 2 * max_width + 16;
+    {   // shared-memory solve: two panel buffers (TMA double buffering) + the pivot / row windows of the vector
+        long long need = 2LL * max_sb_doubles + 4 * 64 + 16;
         solve_smem = (!big.empty() && need <= smem_budget_doubles) ? 1 : 0;
         if (solve_smem) scratch_doubles = (int)std::max<long long>(scratch_doubles, need);
     }
@@ -483,6 +484,9 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             }
         }
     }
+    lcsr_cols.clear();
+    for (int c = 0; c < n; c++)
+        if (lcsr_ptr[c + 1] > lcsr_ptr[c]) lcsr_cols.push_back(c);
     // 6d. flat entry lists of the singleton-leaf phases (coalesced scaling pass of the factorisation)
     leaf_e_off.clear(); leaf_e_col.clear(); leaf_e_pos.clear();
     for (Phase &ph : phases) {

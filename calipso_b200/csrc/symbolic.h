@@ -39,12 +39,8 @@ struct BigTarget {
     int chunk_begin, chunk_end;
     int ldy;                     // leading dimension of Y: rows rounded up to a multiple of 8, plus 4 (=> 8x4 fragment
                                  // loads of the FP64 mma hit 16 distinct shared-memory banks per half-warp)
-    int ldp;                     // leading dimension of the panel work area (rows + w identity rows, same rounding)
-    int tinv_off;                // offset of this supernode's solve block in the Tinv storage:
-                                 //   M  = L_tt^-T D_t^-1   (w x w,  leading dimension ldm, odd => bank-conflict free)
-                                 //   LR = L[R_t, t]        (nR x w, leading dimension ldr, odd), at tinv_off + ldm*w
-    int ldm, ldr;
-    int sb_doubles;              // ldm*w + ldr*w rounded up to even
+    int ldp;                     // leading dimension of the panel work area (same rounding)
+    int panel_doubles;           // size of the supernode's panel in the factor storage (even): one TMA bulk copy in the solves
 };
 struct FwdEntry {                // one (descendant, row) pair of the forward-solve row lists, flattened
     int off;                     // panel offset of L_d[row, 0]
@@ -87,6 +83,7 @@ struct Symbolic {
     std::vector<int> lcsr_col;       // pivot column of the leaf
     std::vector<int> leaf_csr_pos;   // [rows.size()] for entry q of rows[] of a singleton leaf: its position in Lcsr (-1 else)
     long long lcsr_total = 0;
+    std::vector<int> lcsr_cols;      // columns c with lcsr_ptr[c + 1] > lcsr_ptr[c]
     // flat list of the below-diagonal entries of the singleton leaves, grouped by phase, leaf by leaf: panel offset of
     // the entry, pivot column of its leaf, position of its row-ordered copy in Lcsr
     std::vector<int> leaf_e_off, leaf_e_col, leaf_e_pos;
@@ -98,9 +95,9 @@ struct Symbolic {
     std::vector<unsigned> ymask;
     std::vector<int> big_seq;     // shared-memory supernodes in forward schedule order (TMA prefetch chain)
     std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
-    int max_sb_doubles = 0;       // largest solve block
+    int max_sb_doubles = 0;       // largest panel of a shared-memory supernode
     int solve_smem = 0;           // 1: x and two solve-block buffers fit in the CTA work area (ldl_solve fast path)
-    long long tinv_total = 0;     // doubles of Tinv storage per instance
+    long long tinv_total = 0;     // (unused: the solves read the factor panels directly)
     int scratch_doubles = 0;      // shared-memory doubles a CTA needs
     // input entry k of the upper-triangular CSC -> offset in the panel storage
     std::vector<long long> dest;
@@ -110,7 +107,7 @@ struct Symbolic {
     // still postordered (which does not change the fill) so that supernodes are contiguous.
     // Returns an empty string on success, else an error message.
     const char *analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
-                        int smem_budget_doubles = 13500);
+                        int smem_budget_doubles = 9500);   // 76 KB: three CTAs per SM
 };
 
 // Approximate-minimum-degree stand-in: quotient-graph minimum degree with element absorption and exact external

@@ -24,7 +24,7 @@ struct Batch {
     long long ksize;
     double *w, *cand, *step, *res, *err, *corr, *tmp;
     double *grad, *gyx, *hzx, *g, *h, *Wv, *Gv, *Cv, *prod, *bgrad, *lambda;
-    double *panels, *D, *Dinv, *Tinv, *Lcsr, *xs, *rs, *xp, *mgrad, *q, *g0, *h0, *filter, *krylov, *scal;
+    double *panels, *D, *Dinv, *kx, *Lcsr, *xs, *rs, *xp, *mgrad, *q, *g0, *h0, *filter, *krylov, *scal;
     double *Aval, *rhs;
     int *istat;
     long long *prof;
@@ -40,7 +40,7 @@ struct Batch {
         I.Wv = Wv + b * (long long)P.nnzW; I.Gv = Gv + b * (long long)P.nnzG; I.Cv = Cv + b * (long long)P.nnzC;
         I.prod = prod + b * p; I.bgrad = bgrad + b * p; I.lambda = lambda + b * m;
         I.panels = panels + b * P.panel_total; I.D = D + b * N; I.Dinv = Dinv + b * N;
-        I.Tinv = Tinv + b * P.tinv_total;
+        I.kx = kx + b * P.kx_total;
         I.Lcsr = Lcsr + b * P.lcsr_total;
         I.prof = prof ? prof + b * (long long)PROF_COUNT : nullptr;
         I.xs = xs + b * N; I.rs = rs + b * N; I.xp = xp + b * N; I.mgrad = mgrad + b * N;
@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_factor(const __
     double *pan = B.panels + b * P.panel_total;
     double *D = B.D + b * (long long)P.N, *Dinv = B.Dinv + b * (long long)P.N;
     int *istat = B.istat + b * (long long)I_COUNT;
-    if (assemble_generic) matrix_assemble(ctx, P, pan, B.Aval + b * (long long)P.nnzA);
-    ldl_factor(ctx, P, pan, D, Dinv, B.Tinv + b * P.tinv_total, B.Lcsr + b * P.lcsr_total, istat, B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
+    (void)assemble_generic;
+    const double *Ax = B.Aval + b * (long long)P.nnzA;
+    ldl_factor(ctx, P, pan, D, Dinv, KSrc{Ax, Ax, Ax, Ax}, B.Lcsr + b * P.lcsr_total, istat, B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
 __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __g
     if (b >= B.count) return;
     double *rhs = B.rhs + b * (long long)P.N;
     ldl_solve(ctx, P, B.panels + b * P.panel_total, B.D + b * (long long)P.N, B.Dinv + b * (long long)P.N,
-              B.Tinv + b * P.tinv_total, B.Lcsr + b * P.lcsr_total, rhs, rhs, B.xp + b * (long long)P.N, B.istat + b * (long long)I_COUNT,
+              B.kx + b * P.kx_total, B.Lcsr + b * P.lcsr_total, rhs, rhs, B.xp + b * (long long)P.N, B.istat + b * (long long)I_COUNT,
               B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
@@ -174,9 +175,9 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(co
     KERNEL_PROLOGUE
     ProfTimer pt{I.prof, 0};
     pt.start();
-    kkt_assemble(ctx, P, I);
+    kkt_entries(ctx, P, I);
     pt.stop(PROF_ASSEMBLE);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, I.prof);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
     for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
 }
 
@@ -225,6 +226,7 @@ struct cb200_handle {
     ArrayDesc arr[CB200_NUM_ARRAYS]{};
     long long *d_counts = nullptr, *h_counts = nullptr;
     size_t smem_bytes = 0;
+    long long *prof_store = nullptr;
     void *comm = nullptr;
     int nranks = 1;
     int nnzW = 0, nnzG = 0, nnzC = 0;
@@ -299,7 +301,8 @@ static bool finish_batch(cb200_handle *h)
     size_t bytes = (size_t)h->batch * PROF_COUNT * sizeof(long long);
     if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemset(d, 0, bytes) != cudaSuccess) return false;
     h->allocs.push_back(d);
-    h->B.prof = (long long *)d;
+    h->prof_store = (long long *)d;   // counters stay off (B.prof == nullptr) until cb200_get_profile is first called
+    h->B.prof = nullptr;
     h->B.scratch_doubles = h->sym().scratch_doubles;
     h->smem_bytes = (size_t)h->B.scratch_doubles * sizeof(double);
     return true;
@@ -338,7 +341,7 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
     B.Wv = dalloc(h, nnzW, ok); B.Gv = dalloc(h, nnzG, ok); B.Cv = dalloc(h, nnzC, ok);
     B.prod = dalloc(h, p, ok); B.bgrad = dalloc(h, p, ok); B.lambda = dalloc(h, m, ok);
     B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
-    B.Tinv = dalloc(h, P.tinv_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
+    B.kx = dalloc(h, P.kx_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
     B.xs = dalloc(h, N, ok); B.rs = dalloc(h, N, ok); B.xp = dalloc(h, N, ok); B.mgrad = dalloc(h, N, ok);
     B.q = dalloc(h, n, ok); B.g0 = dalloc(h, m, ok); B.h0 = dalloc(h, p, ok);
     B.filter = dalloc(h, 4LL * B.F, ok);
@@ -391,7 +394,7 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     Batch &B = h->B;
     B.count = batch;
     B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
-    B.Tinv = dalloc(h, P.tinv_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
+    B.kx = dalloc(h, P.kx_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
     B.xp = dalloc(h, N, ok); B.Aval = dalloc(h, P.nnzA, ok); B.rhs = dalloc(h, N, ok);
     {
         void *d = nullptr;
@@ -494,6 +497,10 @@ extern "C" int cb200_get_profile(cb200_handle *h, long long *host, int reset)
     CUDA_OK(cudaSetDevice(h->device));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     size_t bytes = (size_t)h->batch * PROF_COUNT * sizeof(long long);
+    if (!h->B.prof) {      // first call switches the counters on (they cost a global read-modify-write per phase)
+        h->B.prof = h->prof_store;
+        CUDA_OK(cudaMemset(h->B.prof, 0, bytes));
+    }
     if (host) CUDA_OK(cudaMemcpy(host, h->B.prof, bytes, cudaMemcpyDeviceToHost));
     if (reset) CUDA_OK(cudaMemset(h->B.prof, 0, bytes));
     return 0;

@@ -9,7 +9,7 @@
 // Reference map (function -> reference file:line it replaces):
 //   cone_eval            cones/cone.jl:71-106, nonnegative.jl:11-15, second_order.jl:13-17
 //   residual_eval        residual.jl:1-51 + norms solve.jl:130-135, optimality_error.jl:1-27
-//   kkt_assemble         residual_jacobian_variables.jl:1-167 (full J never materialised; K written straight into
+//   kkt_entries          residual_jacobian_variables.jl:1-167 (full J never materialised; K gathered straight into
 //                        the supernodal panels = triu! + update_values!, linear_solver.jl:23-24, qdldl.jl:199-213)
 //   ldl_factor           refactor!/QDLDL_factor!, qdldl.jl:269-278,400-589 + compute_inertia!, linear_solver.jl:33-44
 //   ldl_solve            solve!/QDLDL_solve!, qdldl.jl:330-351,592-640
@@ -67,6 +67,10 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const int *lcsr_ptr, *lcsr_col, *leaf_csr_pos;   // row-ordered copy of the singleton-leaf columns
     const int *lcsr_cols;                            // the columns that have singleton-leaf descendants
     int lcsr_ncols;
+    const int *lcsr_rowinfo, *leaf_info;             // packed (16-byte) per-row / per-leaf descriptors of the bulk solve passes
+    // fused assembly (value codes: array id << 30 | offset, see KSrc)
+    const int *leaf_e_src, *leaf_piv_src, *basm_src, *basm_dst, *gasm_src, *gasm_dst, *gasm_zero;
+    int n_gasm, n_gasm_zero;
     long long lcsr_total;
     const int *leaf_e_off, *leaf_e_col, *leaf_e_pos;   // flat below-diagonal entries of the singleton leaves
     const int *big_index;                      // [ns] -> big[] (shared-memory path) or -1
@@ -74,7 +78,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const YChunk *ychunks;
     const int *ystage_src, *ystage_dst, *ypiv;
     const unsigned *ymask;
-    long long tinv_total;
+    long long kx_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
     int nbig, max_sb_doubles, solve_smem;
     // assembly destinations (offsets into the panel storage)
@@ -129,7 +133,7 @@ struct Inst {         // device pointers of ONE instance
     double *Wv, *Gv, *Cv;                              // values at the patterns
     double *prod, *bgrad;                              // [p]
     double *lambda;                                    // [m]
-    double *panels, *D, *Dinv, *Tinv, *Lcsr;           // factor (+ M blocks of the big supernodes, leaf CSR copy)
+    double *panels, *D, *Dinv, *kx, *Lcsr;           // factor (+ M blocks of the big supernodes, leaf CSR copy)
     long long *prof;                                   // [PROF_COUNT] cycle counters (may be null)
     double *xs, *rs, *xp;                              // [N] reduced solution / rhs / permuted scratch
     double *mgrad;                                     // [N]
@@ -139,6 +143,18 @@ struct Inst {         // device pointers of ONE instance
     double *scal;                                      // [S_COUNT]
     int *istat;                                        // [I_COUNT]
 };
+
+// The value arrays the assembly codes refer to.  KKT handles: W, G, C values at their patterns and the computed
+// entries kx (kkt_entries); LinearSolver-seam handles: a0 = the caller's matrix values.
+struct KSrc {
+    const double *a0, *a1, *a2, *a3;
+};
+CB_DEV double ksrc_load(const KSrc &K, int code)
+{
+    const unsigned id = (unsigned)code >> 30;
+    const double *base = id == 0 ? K.a0 : (id == 1 ? K.a1 : (id == 2 ? K.a2 : K.a3));
+    return base[code & 0x3fffffff];
+}
 
 // ------------------------------------------------------------------------------------------------ cooperation scope
 struct Ctx {
@@ -222,6 +238,27 @@ template <class F> CB_DEV double scope_max(const Ctx &ctx, int n, F f)
 template <class F> CB_DEV int scope_any(const Ctx &ctx, int n, F f)
 {
     return scope_max(ctx, n, [&](int i) { return f(i) ? 1.0 : 0.0; }) > 0.5;
+}
+
+// Sparse rows handled by groups of G lanes (G = 4: 64 rows of a 256-thread CTA in flight, short dependent-load chains):
+// part(row, sub, G) returns the lane's partial sum over the entries sub, sub + G, ... of the row, fin(row, sum) runs on
+// the group's first lane.  Fixed association order.  Host emulation: one "lane" per row.
+template <int G, class Part, class Fin> CB_DEV void grouped_rows(const Ctx &ctx, int nrows, Part part, Fin fin)
+{
+#if CB_ON_DEVICE
+    if (!ctx.warp_scope) {
+        const int sub = threadIdx.x & (G - 1), grp = threadIdx.x / G, ngrp = blockDim.x / G;
+        const int padded = (nrows + ngrp - 1) / ngrp * ngrp;      // every warp runs every shuffle
+        for (int r = grp; r < padded; r += ngrp) {
+            double acc = r < nrows ? part(r, sub, G) : 0.0;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (sub == 0 && r < nrows) fin(r, acc);
+        }
+        return;
+    }
+#endif
+    PAR_FOR(r, nrows) fin(r, part(r, 0, 1));
 }
 
 // ------------------------------------------------------------------------------------------------ second-order cone algebra
@@ -376,58 +413,28 @@ CB_DEV void merit_gradient(const Ctx &ctx, const DevProblem &P, const Inst &I)
 }
 
 // ------------------------------------------------------------------------------------------------ KKT assembly
-// pan[dst[k]] = val[k]: four independent gathers in flight per thread (the stores cannot be reordered by the compiler
-// past the loads of the next iteration otherwise)
-CB_DEV void scatter_values(const Ctx &ctx, double *__restrict__ pan, const long long *__restrict__ dst,
-                           const double *__restrict__ val, int count)
-{
-#if CB_ON_DEVICE
-    int k = ctx.tid;
-    const int st = ctx.nthr;
-    for (; k + 3 * st < count; k += 4 * st) {
-        const long long d0 = dst[k], d1 = dst[k + st], d2 = dst[k + 2 * st], d3 = dst[k + 3 * st];
-        const double v0 = val[k], v1 = val[k + st], v2 = val[k + 2 * st], v3 = val[k + 3 * st];
-        pan[d0] = v0; pan[d1] = v1; pan[d2] = v2; pan[d3] = v3;
-    }
-    for (; k < count; k += st) pan[dst[k]] = val[k];
-#else
-    for (int k = 0; k < count; k++) pan[dst[k]] = val[k];
-#endif
-}
-
-// Writes the upper triangle of the reduced matrix K straight into the (zeroed) supernodal
-// panels.  eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.
-CB_DEVN void kkt_assemble(const Ctx &ctx, const DevProblem &P, const Inst &I)
+// The entries of the reduced matrix K that are not plain copies of W, G, C values:
+// kx = [W diagonal + eps_p | y diagonal | nonnegative z diagonal | upper triangles of the second-order z blocks].
+// eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.  The matrix itself
+// is never stored: the factorisation gathers W, G, C values and these entries straight into its panels (triu! +
+// update_values!, linear_solver.jl:23-24, qdldl.jl:199-213, fused with refactor!).
+CB_DEVN void kkt_entries(const Ctx &ctx, const DevProblem &P, const Inst &I)
 {
     const double ep = I.scal[S_EPSP], ed = I.scal[S_EPSD], rho = I.scal[S_RHO];
     const double *s = I.w + P.n + P.m, *t = I.w + P.n + 2 * P.m + 2 * P.p;
-    double *pan = I.panels;
-    {   // zero (two doubles per store; panel_total is even)
-        long long n2 = P.panel_total / 2;
-#if CB_ON_DEVICE
-        double2 *p2 = reinterpret_cast<double2 *>(pan);
-        for (long long i = ctx.tid; i < n2; i += ctx.nthr) p2[i] = make_double2(0.0, 0.0);
-#else
-        for (long long i = 0; i < 2 * n2; i++) pan[i] = 0.0;
-#endif
-    }
-    ctx.sync();
-    scatter_values(ctx, pan, P.dW, I.Wv, P.nnzW);
-    scatter_values(ctx, pan, P.dG, I.Gv, P.nnzG);
-    scatter_values(ctx, pan, P.dC, I.Cv, P.nnzC);
+    double *kw = I.kx, *ky = kw + P.n, *kz = ky + P.m, *ks = kz + P.q_nn;
     const double Jrr = rho + ep, Jyy = -ed, Jzz = -ed, Jss = ep;
-    PAR_FOR(i, P.m) pan[P.dY[i]] = -1.0 / Jrr + Jyy;
+    PAR_FOR(j, P.n) kw[j] = I.Wv[P.Wdiag[j]] + ep;
+    PAR_FOR(i, P.m) ky[i] = -1.0 / Jrr + Jyy;
     PAR_FOR(i, P.q_nn) {
         double Sb = s[i] - ed, Ti = t[i];
-        pan[P.dZnn[i]] = -1.0 * Sb / (Ti + Sb * Jss) + Jzz;
+        kz[i] = -1.0 * Sb / (Ti + Sb * Jss) + Jzz;
     }
-    ctx.sync();
-    PAR_FOR(j, P.n) pan[P.dW[P.Wdiag[j]]] += ep;
     // SOC blocks: column j (rows i <= j) of -(arrow(u))^-1 Sbar + D, u = first row of T + Sbar*P
     PAR_FOR(k, P.nsoc) {
         int d = P.soc_dims[k];
         const double *sk = s + P.soc_off[k], *tk = t + P.soc_off[k];
-        const long long *dst = P.dZsoc + P.soc_tri[k];
+        double *dst = ks + P.soc_tri[k];
         auto u = [&](int i) { return i == 0 ? tk[0] + (sk[0] - ed) * Jss : tk[i] + sk[i] * Jss; };
         int tri = 0;
         for (int j = 0; j < d; j++) {
@@ -440,27 +447,12 @@ CB_DEVN void kkt_assemble(const Ctx &ctx, const DevProblem &P, const Inst &I)
                     double e = 0.0;
                     e -= v;
                     if (i == j) e += Jzz;
-                    pan[dst[tri + i]] = e;
+                    dst[tri + i] = e;
                 }
             });
             tri += j + 1;
         }
     }
-    ctx.sync();
-}
-
-// generic-matrix mode (LinearSolver seam): scatter the caller's upper-triangle values
-CB_DEVN void matrix_assemble(const Ctx &ctx, const DevProblem &P, double *pan, const double *Ax)
-{
-    long long n2 = P.panel_total / 2;
-#if CB_ON_DEVICE
-    double2 *p2 = reinterpret_cast<double2 *>(pan);
-    for (long long i = ctx.tid; i < n2; i += ctx.nthr) p2[i] = make_double2(0.0, 0.0);
-#else
-    for (long long i = 0; i < 2 * n2; i++) pan[i] = 0.0;
-#endif
-    ctx.sync();
-    scatter_values(ctx, pan, P.dA, Ax, P.nnzA);
     ctx.sync();
 }
 
@@ -693,7 +685,7 @@ __device__ __forceinline__ void panel_factor_tc(double *__restrict__ S, int rows
 // the staging lists carry the pivots of the Y columns as extra entries (src < 0 -> D[-1 - src]); the Y area is reused
 // by the panel factorisation (U, reciprocals, pivots, unscaled multipliers).
 CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv,
-                                 double *Tinv, int s, const BigTarget bt, ProfTimer &pt)
+                                 const KSrc &K, int s, const BigTarget bt, ProfTimer &pt)
 {
     const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
     const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
@@ -701,24 +693,46 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
     double *Ps = pan + P.panel_off[s];
     double *S = CB_SCRATCH(ctx);
     double *Y = S + (long long)ldp * w;
-    (void)Tinv;
     pt.start();
+    // fused assembly: clear the work area and gather the supernode's input entries (W values, computed entries)
 #if CB_ON_DEVICE
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    // the assembled panel streams into shared memory asynchronously (LDGSTS) while the first chunk is staged
-    for (int k = wid; k < w; k += nw) {
-        const double *src = Ps + k * nrow;
-        double *dst = S + k * ldp;
-        for (int i = lane; i < nrow; i += 32) cp_async8(dst + i, src + i);
-        for (int i = nrow + lane; i < ldp; i += 32) dst[i] = 0.0;
+    {
+        const int na = bt.asm_end - bt.asm_begin, nthr = ctx.nthr;
+        const int *__restrict__ asrc = P.basm_src + bt.asm_begin, *__restrict__ adst = P.basm_dst + bt.asm_begin;
+        int sc[4], dc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {          // first batch of indices in flight while S is cleared
+            const int ee = ctx.tid + u * nthr;
+            sc[u] = ee < na ? asrc[ee] : 0;
+            dc[u] = ee < na ? adst[ee] : -1;
+        }
+        double2 *S2 = reinterpret_cast<double2 *>(S);
+        const int n2 = (ldp * w) >> 1;          // ldp is a multiple of 4
+        for (int e = ctx.tid; e < n2; e += nthr) S2[e] = make_double2(0.0, 0.0);
+        __syncthreads();
+        for (int e = ctx.tid;;) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = dc[u] >= 0 ? ksrc_load(K, sc[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (dc[u] >= 0) S[dc[u]] = v[u];
+            e += 4 * nthr;
+            if (e >= na) break;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int ee = e + u * nthr;
+                sc[u] = ee < na ? asrc[ee] : 0;
+                dc[u] = ee < na ? adst[ee] : -1;
+            }
+        }
     }
-    bool panel_pending = true;
 #else
-    PAR_FOR(e, ldp * w) {
-        int k = e / ldp, i = e % ldp;
-        S[e] = i < nrow ? Ps[i + (long long)k * nrow] : 0.0;
-    }
+    PAR_FOR(e, ldp * w) S[e] = 0.0;
+    PAR_FOR(e, bt.asm_end - bt.asm_begin) S[P.basm_dst[bt.asm_begin + e]] = ksrc_load(K, P.basm_src[bt.asm_begin + e]);
 #endif
+    ctx.sync();
     for (int ci = bt.chunk_begin; ci < bt.chunk_end; ci++) {
         const YChunk ch = P.ychunks[ci];
         const int kc = ch.col_end - ch.col_begin, kc4 = (kc + 3) & ~3;
@@ -757,7 +771,6 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
                     didx[u] = ee < nst ? dst[ee] : 0;
                 }
             }
-            if (panel_pending) { cp_async_wait_all(); panel_pending = false; }
         }
 #else
         PAR_FOR(e, (ldy + 1) * kc4) Y[e] = 0.0;
@@ -784,15 +797,24 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
                     const double *ya = Y + 8 * ti + gid + tig * ldy, *yb = Y + 8 * tj + gid + tig * ldy;
                     const double *dy = Dy + tig;
                     double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-                    while (m) {
-                        const int g = __ffs(m) - 1;
-                        m &= m - 1;
-                        dmma_8x8x4(e0, e1, ya[4 * g * ldy], yb[4 * g * ldy] * dy[4 * g]);
-                        if (m) {
-                            const int g2 = __ffs(m) - 1;
+                    while (m) {      // four column groups per round: twelve shared-memory loads in flight
+                        int g[4];
+                        double av[4], bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            g[u] = m ? __ffs(m) - 1 : -1;
                             m &= m - 1;
-                            dmma_8x8x4(f0, f1, ya[4 * g2 * ldy], yb[4 * g2 * ldy] * dy[4 * g2]);
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int go = 4 * max(g[u], 0);
+                            av[u] = ya[go * ldy];
+                            bv[u] = g[u] >= 0 ? yb[go * ldy] * dy[go] : 0.0;
+                        }
+                        dmma_8x8x4(e0, e1, av[0], bv[0]);
+                        dmma_8x8x4(f0, f1, av[1], bv[1]);
+                        dmma_8x8x4(e0, e1, av[2], bv[2]);
+                        dmma_8x8x4(f0, f1, av[3], bv[3]);
                     }
                     const int r = 8 * ti + gid, col = 8 * tj + 2 * tig;
                     if (r < nrow) {
@@ -817,9 +839,6 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_GEMM);
     }
-#if CB_ON_DEVICE
-    if (panel_pending) { cp_async_wait_all(); __syncthreads(); }
-#endif
     double *dd = Y + 72;                 // w pivots
 #if CB_ON_DEVICE
     if (nrow <= (int)blockDim.x) {
@@ -887,56 +906,63 @@ template <class F, class G> CB_DEV void for_each_supernode(const Ctx &cta, const
 }
 
 // numeric factorisation + inertia (positive = #(D>0), negative = #(D<=0), zero = #(D==0); linear_solver.jl:33-44)
-CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, double *Tinv,
+CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double *D, double *Dinv, const KSrc &K,
                         double *Lcsr, int *istat, long long *prof)
 {
     ProfTimer pt{prof, 0};
     pt.start();
+    // supernodes off the shared-memory path are assembled in the factor storage: clear their panels, gather their entries
+    PAR_FOR(e, P.n_gasm_zero) pan[P.gasm_zero[e]] = 0.0;
+    ctx.sync();
+    PAR_FOR(e, P.n_gasm) pan[P.gasm_dst[e]] = ksrc_load(K, P.gasm_src[e]);
+    ctx.sync();
+    pt.stop(PROF_ASSEMBLE);
     for_each_supernode(
         ctx, P, true,
         [&](const Ctx &c, int s) {
             const int bi = (c.warp_scope || !P.big_index) ? -1 : P.big_index[s];
-            if (bi >= 0 && c.scratch) {
-                factor_supernode_big(c, P, pan, D, Dinv, Tinv, s, P.big[bi], pt);
+            if (bi >= 0) {
+                factor_supernode_big(c, P, pan, D, Dinv, K, s, P.big[bi], pt);
             } else {
                 factor_supernode(c, P, pan, D, Dinv, s);
                 if (!c.warp_scope) pt.stop(PROF_FACTOR_BIG_GENERIC);
             }
         },
-        [&](const Ctx &ctx, int begin, int end, int ebegin, int eend) {   // singleton leaves: L = a / d
+        [&](const Ctx &ctx, int begin, int end, int ebegin, int eend) {   // singleton leaves: L = a / d, straight from the input values
             pt.stop(PROF_FACTOR_SMALL);
             PAR_FOR(q, end - begin) {       // pivots
                 const int s = P.order[begin + q], c0 = P.sn_start[s];
-                const double dk = pan[P.panel_off[s]];
+                const double dk = ksrc_load(K, P.leaf_piv_src[begin + q]);
+                pan[P.panel_off[s]] = dk;
                 D[c0] = dk;
                 Dinv[c0] = dk != 0.0 ? 1.0 / dk : 0.0;
             }
             ctx.sync();
             {                               // entries, leaf by leaf => coalesced panel accesses
                 const int *__restrict__ eo = P.leaf_e_off + ebegin, *__restrict__ ec = P.leaf_e_col + ebegin,
-                                        *__restrict__ ep = P.leaf_e_pos + ebegin;
+                                        *__restrict__ ep = P.leaf_e_pos + ebegin, *__restrict__ es = P.leaf_e_src + ebegin;
                 const int cnt = eend - ebegin;
 #if CB_ON_DEVICE
                 int e = ctx.tid;
                 const int st = ctx.nthr;
                 for (; e + 3 * st < cnt; e += 4 * st) {
-                    int o[4], pp[4];
+                    int o[4], pp[4], sc[4], cc[4];
                     double v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { o[u] = eo[e + u * st]; pp[u] = ep[e + u * st]; }
+                    for (int u = 0; u < 4; u++) { o[u] = eo[e + u * st]; pp[u] = ep[e + u * st]; sc[u] = es[e + u * st]; cc[u] = ec[e + u * st]; }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = pan[o[u]] * Dinv[ec[e + u * st]];
+                    for (int u = 0; u < 4; u++) v[u] = ksrc_load(K, sc[u]) * Dinv[cc[u]];
 #pragma unroll
                     for (int u = 0; u < 4; u++) { pan[o[u]] = v[u]; Lcsr[pp[u]] = v[u]; }
                 }
                 for (; e < cnt; e += st) {
-                    const double l = pan[eo[e]] * Dinv[ec[e]];
+                    const double l = ksrc_load(K, es[e]) * Dinv[ec[e]];
                     pan[eo[e]] = l;
                     Lcsr[ep[e]] = l;
                 }
 #else
                 for (int e = 0; e < cnt; e++) {
-                    const double l = pan[eo[e]] * Dinv[ec[e]];
+                    const double l = ksrc_load(K, es[e]) * Dinv[ec[e]];
                     pan[eo[e]] = l;
                     Lcsr[ep[e]] = l;     // row-ordered copy for the bulk forward pass
                 }
@@ -1003,22 +1029,19 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     __syncthreads();
     if (P.nbig > 0) issue(0);
     // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final);
-    // eight lanes per column, columns without leaf descendants are not visited
+    // four lanes per column, columns without leaf descendants are not visited
     {
-        const int sub = tid & 7, grp = tid >> 3, ngrp = nthr >> 3;
-        for (int ci = grp; ci < P.lcsr_ncols + ((-P.lcsr_ncols) & (ngrp - 1)); ci += ngrp) {   // whole warps stay together
-            double acc = 0.0;
-            int cidx = -1;
-            if (ci < P.lcsr_ncols) {
-                cidx = P.lcsr_cols[ci];
-                const int q0 = P.lcsr_ptr[cidx], q1 = P.lcsr_ptr[cidx + 1];
-                for (int q = q0 + sub; q < q1; q += 8) acc += Lcsr[q] * xp[P.lcsr_col[q]];
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            if (sub == 0 && cidx >= 0) xp[cidx] -= acc;
-        }
+        const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.lcsr_rowinfo);
+        const int *__restrict__ lcol = P.lcsr_col;
+        grouped_rows<4>(
+            ctx, P.lcsr_ncols,
+            [&](int r, int sub, int st) {
+                const int4 ri = info[r];
+                double acc = 0.0;
+                for (int q = ri.y + sub; q < ri.z; q += st) acc += Lcsr[q] * xp[lcol[q]];
+                return acc;
+            },
+            [&](int r, double acc) { xp[info[r].x] -= acc; });
     }
     __syncthreads();
     int pos = 0;
@@ -1158,25 +1181,20 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             }
             ctx.sync();
         },
-        [&](const Ctx &, int begin, int end, int, int) {   // singleton leaves: eight lanes per leaf
-            const int sub = tid & 7, grp = tid >> 3, ngrp = nthr >> 3;
-            const int cnt = end - begin;
-            for (int q = grp; q < cnt + ((-cnt) & (ngrp - 1)); q += ngrp) {
-                double acc = 0.0;
-                int c0 = -1;
-                if (q < cnt) {
-                    const int s = P.order[begin + q];
-                    c0 = P.sn_start[s];
-                    const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s];
-                    const double *col = pan + P.panel_off[s] + 1;
-                    const int *__restrict__ R = P.rows + P.rows_ptr[s];
-                    for (int i = sub; i < nR; i += 8) acc += col[i] * xp[R[i]];
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                if (sub == 0 && c0 >= 0) xp[c0] -= acc;
-            }
+        [&](const Ctx &c, int begin, int end, int, int) {   // singleton leaves: four lanes per leaf
+            const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.leaf_info) + begin;
+            const int *__restrict__ rows = P.rows;
+            grouped_rows<4>(
+                c, end - begin,
+                [&](int q, int sub, int st) {
+                    const int4 li = info[q];        // pivot column, |R|, panel offset, rows offset
+                    const double *__restrict__ col = pan + li.z;
+                    const int *__restrict__ R = rows + li.w;
+                    double acc = 0.0;
+                    for (int i = sub; i < li.y; i += st) acc += col[i] * xp[R[i]];
+                    return acc;
+                },
+                [&](int q, double acc) { xp[info[q].x] -= acc; });
             __syncthreads();
         });
     for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xp[k];
@@ -1192,7 +1210,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
 // Supernodes on the shared-memory path use M = L_tt^-T D_t^-1 (stored by the factorisation) so that their triangular
 // solves are mat-vecs: forward y_t = D_t M' v, backward x_t = M (D_t v).
 CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, const double *D, const double *Dinv,
-                       const double *Tinv, const double *Lcsr, const double *b, double *x, double *xp, int *istat,
+                       const double *kx, const double *Lcsr, const double *b, double *x, double *xp, int *istat,
                        long long *prof)
 {
 #if CB_ON_DEVICE
@@ -1376,18 +1394,32 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
     const double *s = I.w + n + m, *t = I.w + n + 2 * m + 2 * p;
     const double *vx = v, *vr = v + n, *vs = v + n + m, *vy = v + n + m + p, *vz = v + n + 2 * m + p,
                  *vt = v + n + 2 * m + 2 * p;
-    PAR_FOR(i, n) {
-        double a = ep * vx[i];
-        for (int k = P.Wfull.ptr[i]; k < P.Wfull.ptr[i + 1]; k++) a += I.Wv[P.Wfull.src[k]] * vx[P.Wfull.col[k]];
-        for (int k = P.Gp[i]; k < P.Gp[i + 1]; k++) a += I.Gv[k] * vy[P.Gi[k]];
-        for (int k = P.Cp[i]; k < P.Cp[i + 1]; k++) a += I.Cv[k] * vz[P.Ci[k]];
-        out[i] = a;
-    }
-    PAR_FOR(i, m) {
-        out[n + i] = (rho + ep) * vr[i] - vy[i];
-        double a = 0.0;
-        for (int k = P.Grow.ptr[i]; k < P.Grow.ptr[i + 1]; k++) a += I.Gv[P.Grow.src[k]] * vx[P.Grow.col[k]];
-        out[n + m + p + i] = a - vr[i] - ed * vy[i];
+    {
+        const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col, *__restrict__ ws = P.Wfull.src;
+        const int *__restrict__ gp = P.Gp, *__restrict__ gi = P.Gi, *__restrict__ cp = P.Cp, *__restrict__ ci = P.Ci;
+        const double *__restrict__ Wv = I.Wv, *__restrict__ Gv = I.Gv, *__restrict__ Cv = I.Cv;
+        grouped_rows<4>(
+            ctx, n,
+            [&](int i, int sub, int st) {
+                double a = 0.0;
+                for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += Wv[ws[k]] * vx[wc[k]];
+                for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += Gv[k] * vy[gi[k]];
+                for (int k = cp[i] + sub; k < cp[i + 1]; k += st) a += Cv[k] * vz[ci[k]];
+                return a;
+            },
+            [&](int i, double a) { out[i] = ep * vx[i] + a; });
+        const int *__restrict__ grp = P.Grow.ptr, *__restrict__ grc = P.Grow.col, *__restrict__ grs = P.Grow.src;
+        grouped_rows<4>(
+            ctx, m,
+            [&](int i, int sub, int st) {
+                double a = 0.0;
+                for (int k = grp[i] + sub; k < grp[i + 1]; k += st) a += Gv[grs[k]] * vx[grc[k]];
+                return a;
+            },
+            [&](int i, double a) {
+                out[n + i] = (rho + ep) * vr[i] - vy[i];
+                out[n + m + p + i] = a - vr[i] - ed * vy[i];
+            });
     }
     PAR_FOR(i, p) {
         out[n + m + i] = ep * vs[i] - vz[i] - vt[i];
@@ -1413,9 +1445,9 @@ CB_DEV bool factorize_regularized(const Ctx &ctx, const DevProblem &P, const Ins
 {
     ProfTimer pt{I.prof, 0};
     pt.start();
-    kkt_assemble(ctx, P, I);
+    kkt_entries(ctx, P, I);
     pt.stop(PROF_ASSEMBLE);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, I.prof);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
     bool ok = I.istat[I_INERTIA_POS] == P.n && I.istat[I_INERTIA_NEG] == P.m + P.p && I.istat[I_INERTIA_ZERO] == 0;
     ctx.sync();
     if (ctx.tid == 0) I.istat[I_TRIALS]++;
@@ -1463,7 +1495,7 @@ CB_DEV void direction_symmetric(const Ctx &ctx, const DevProblem &P, const Inst 
     pt.start();
     reduced_rhs(ctx, P, I, res, I.rs);
     pt.stop(PROF_RHS_RECOVER);
-    ldl_solve(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.rs, I.xs, I.xp, I.istat, I.prof);
+    ldl_solve(ctx, P, I.panels, I.D, I.Dinv, I.kx, I.Lcsr, I.rs, I.xs, I.xp, I.istat, I.prof);
     pt.start();
     recover_step(ctx, P, I, res, I.xs, step);
     pt.stop(PROF_RHS_RECOVER);

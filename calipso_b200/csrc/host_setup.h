@@ -117,6 +117,21 @@ struct HostProblem {
             return d;
         };
         dW = gather(eW); dG = gather(eG); dC = gather(eC); dY = gather(eY); dZnn = gather(eZnn); dZsoc = gather(eZsoc);
+        // value codes of the fused assembly: array id << 30 | offset with arrays 0 = W values, 1 = G values,
+        // 2 = C values, 3 = computed entries kx = [W diagonal + eps_p (n) | y diagonal (m) | nonnegative z diagonal (q_nn) |
+        // second-order z blocks (tri_total)]
+        {
+            std::vector<int> code(Ki.size(), -1);
+            for (int k = 0; k < nnzW; k++) code[eW[k]] = k;
+            for (int j = 0; j < n; j++) code[eW[Wdiag[j]]] = (int)((3u << 30) | (unsigned)j);
+            for (int k = 0; k < nnzG; k++) code[eG[k]] = (1 << 30) | k;
+            for (int k = 0; k < nnzC; k++) code[eC[k]] = (int)((2u << 30) | (unsigned)k);
+            for (int i = 0; i < m; i++) code[eY[i]] = (int)((3u << 30) | (unsigned)(n + i));
+            for (int i = 0; i < q_nn; i++) code[eZnn[i]] = (int)((3u << 30) | (unsigned)(n + m + i));
+            for (int t = 0; t < tri; t++) code[eZsoc[t]] = (int)((3u << 30) | (unsigned)(n + m + q_nn + t));
+            sym.map_sources([&](int e) { return code[e]; });
+            sym.kx_total = (long long)n + m + q_nn + tri;
+        }
         return "";
     }
 };
@@ -154,12 +169,17 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.order = up(S.order); P.phases = up(S.phases); P.fwd_ptr = up(S.fwd_ptr); P.fwd = up(S.fwd);
     P.big_index = up(S.big_index); P.big = up(S.big); P.ychunks = up(S.ychunks);
     P.ystage_src = up(S.ystage_src); P.ystage_dst = up(S.ystage_dst); P.ypiv = up(S.ypiv); P.ymask = up(S.ymask);
-    P.tinv_total = S.tinv_total;
+    P.kx_total = S.kx_total;
     P.big_seq = up(S.big_seq); P.big_seq_bwd = up(S.big_seq_bwd); P.nbig = (int)S.big_seq.size(); P.max_sb_doubles = S.max_sb_doubles;
     P.solve_smem = S.solve_smem;
     P.lcsr_ptr = up(S.lcsr_ptr); P.lcsr_col = up(S.lcsr_col); P.leaf_csr_pos = up(S.leaf_csr_pos);
     P.lcsr_total = S.lcsr_total;
     P.lcsr_cols = up(S.lcsr_cols); P.lcsr_ncols = (int)S.lcsr_cols.size();
+    P.lcsr_rowinfo = up(S.lcsr_rowinfo); P.leaf_info = up(S.leaf_info);
+    P.leaf_e_src = up(S.leaf_e_src); P.leaf_piv_src = up(S.leaf_piv_src);
+    P.basm_src = up(S.basm_src); P.basm_dst = up(S.basm_dst);
+    P.gasm_src = up(S.gasm_src); P.gasm_dst = up(S.gasm_dst); P.gasm_zero = up(S.gasm_zero);
+    P.n_gasm = (int)S.gasm_src.size(); P.n_gasm_zero = (int)S.gasm_zero.size();
     P.leaf_e_off = up(S.leaf_e_off); P.leaf_e_col = up(S.leaf_e_col); P.leaf_e_pos = up(S.leaf_e_pos);
 }
 

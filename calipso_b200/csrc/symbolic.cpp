@@ -368,7 +368,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     big_index.assign(ns, -1);
     big.clear(); ychunks.clear(); ystage_src.clear(); ystage_dst.clear(); ypiv.clear(); ymask.clear(); big_seq.clear();
     max_sb_doubles = 0;
-    tinv_total = 0;
+    kx_total = 0;
     scratch_doubles = 0;
     for (const Phase &ph : phases) {
         if (ph.mode != 1 || panel_total > 2000000000LL) continue;
@@ -395,6 +395,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             bt.ldy = ldy;
             bt.ldp = ldp;
             bt.panel_doubles = (int)(panel_off[t + 1] - panel_off[t]);
+            bt.asm_begin = bt.asm_end = 0;
             int col = 0;
             YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
             ymask.resize(ymask.size() + ntI, 0u);
@@ -485,8 +486,23 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         }
     }
     lcsr_cols.clear();
+    lcsr_rowinfo.clear();
     for (int c = 0; c < n; c++)
-        if (lcsr_ptr[c + 1] > lcsr_ptr[c]) lcsr_cols.push_back(c);
+        if (lcsr_ptr[c + 1] > lcsr_ptr[c]) {
+            lcsr_cols.push_back(c);
+            lcsr_rowinfo.insert(lcsr_rowinfo.end(), {c, lcsr_ptr[c], lcsr_ptr[c + 1], 0});
+        }
+    leaf_info.assign(4 * (size_t)ns, 0);
+    for (const Phase &ph : phases) {
+        if (ph.mode != 2) continue;
+        for (int q = ph.begin; q < ph.end; q++) {
+            const int t = order[q];
+            leaf_info[4 * (size_t)q + 0] = sn_start[t];
+            leaf_info[4 * (size_t)q + 1] = rows_ptr[t + 1] - rows_ptr[t];
+            leaf_info[4 * (size_t)q + 2] = (int)(panel_off[t] + 1);
+            leaf_info[4 * (size_t)q + 3] = rows_ptr[t];
+        }
+    }
     // 6d. flat entry lists of the singleton-leaf phases (coalesced scaling pass of the factorisation)
     leaf_e_off.clear(); leaf_e_col.clear(); leaf_e_pos.clear();
     for (Phase &ph : phases) {
@@ -522,6 +538,44 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             }
             dest[q] = panel_off[s] + (long long)(c - sn_start[s]) * nrow + lr;
         }
+    // 8. fused-assembly lists
+    if (panel_total > 2000000000LL) return "factor storage exceeds 2^31 entries";
+    {
+        std::vector<int> entry_at((size_t)panel_total, -1);
+        for (int q = 0; q < nnzA; q++) entry_at[(size_t)dest[q]] = q;
+        leaf_e_src.assign(leaf_e_off.size(), -1);
+        for (size_t e = 0; e < leaf_e_off.size(); e++) {
+            leaf_e_src[e] = entry_at[(size_t)leaf_e_off[e]];
+            if (leaf_e_src[e] < 0) return "internal error: leaf entry without an input entry";
+        }
+        leaf_piv_src.assign(ns, -1);
+        basm_src.clear(); basm_dst.clear(); gasm_src.clear(); gasm_dst.clear(); gasm_zero.clear();
+        std::vector<char> is_leaf(ns, 0);
+        for (const Phase &ph : phases)
+            if (ph.mode == 2)
+                for (int q = ph.begin; q < ph.end; q++) {
+                    is_leaf[order[q]] = 1;
+                    leaf_piv_src[q] = entry_at[(size_t)panel_off[order[q]]];
+                }
+        for (int t = 0; t < ns; t++) {
+            if (is_leaf[t]) continue;
+            const int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
+            const int bi = big_index[t];
+            if (bi >= 0) big[bi].asm_begin = (int)basm_src.size();
+            for (int k = 0; k < w; k++)
+                for (int i = 0; i < nrow; i++) {
+                    const long long off = panel_off[t] + (long long)k * nrow + i;
+                    const int q = entry_at[(size_t)off];
+                    if (bi >= 0) {
+                        if (q >= 0) { basm_src.push_back(q); basm_dst.push_back(k * big[bi].ldp + i); }
+                    } else {
+                        gasm_zero.push_back((int)off);
+                        if (q >= 0) { gasm_src.push_back(q); gasm_dst.push_back((int)off); }
+                    }
+                }
+            if (bi >= 0) big[bi].asm_end = (int)basm_src.size();
+        }
+    }
     return "";
 }
 

@@ -41,6 +41,7 @@ struct BigTarget {
                                  // loads of the FP64 mma hit 16 distinct shared-memory banks per half-warp)
     int ldp;                     // leading dimension of the panel work area (same rounding)
     int panel_doubles;           // size of the supernode's panel in the factor storage (even): one TMA bulk copy in the solves
+    int asm_begin, asm_end;      // range in basm_src / basm_dst: the input entries of this supernode (fused assembly)
 };
 struct FwdEntry {                // one (descendant, row) pair of the forward-solve row lists, flattened
     int off;                     // panel offset of L_d[row, 0]
@@ -84,6 +85,9 @@ struct Symbolic {
     std::vector<int> leaf_csr_pos;   // [rows.size()] for entry q of rows[] of a singleton leaf: its position in Lcsr (-1 else)
     long long lcsr_total = 0;
     std::vector<int> lcsr_cols;      // columns c with lcsr_ptr[c + 1] > lcsr_ptr[c]
+    std::vector<int> lcsr_rowinfo;   // 4 ints per such column: c, lcsr_ptr[c], lcsr_ptr[c + 1], 0 (one 16-byte load)
+    std::vector<int> leaf_info;      // 4 ints per position of order[] that holds a singleton leaf: pivot column, |R|,
+                                     // panel offset of its first below-diagonal entry, offset of R in rows[]
     // flat list of the below-diagonal entries of the singleton leaves, grouped by phase, leaf by leaf: panel offset of
     // the entry, pivot column of its leaf, position of its row-ordered copy in Lcsr
     std::vector<int> leaf_e_off, leaf_e_col, leaf_e_pos;
@@ -97,10 +101,24 @@ struct Symbolic {
     std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
     int max_sb_doubles = 0;       // largest panel of a shared-memory supernode
     int solve_smem = 0;           // 1: x and two solve-block buffers fit in the CTA work area (ldl_solve fast path)
-    long long tinv_total = 0;     // (unused: the solves read the factor panels directly)
+    long long kx_total = 0;     // (unused: the solves read the factor panels directly)
     int scratch_doubles = 0;      // shared-memory doubles a CTA needs
     // input entry k of the upper-triangular CSC -> offset in the panel storage
     std::vector<long long> dest;
+    // Fused assembly: the factorisation reads the input values itself instead of a pre-assembled panel storage.
+    // Sources are input-entry indices here; HostProblem::build rewrites them into value codes (array id << 30 | offset).
+    std::vector<int> leaf_e_src;             // per flat leaf entry (see leaf_e_off)
+    std::vector<int> leaf_piv_src;           // [ns] per position of order[]: pivot entry of a singleton leaf
+    std::vector<int> basm_src, basm_dst;     // shared-memory supernodes: (input entry, offset in the work area S)
+    std::vector<int> gasm_src, gasm_dst;     // all other supernodes: (input entry, panel offset), assembled in global memory
+    std::vector<int> gasm_zero;              // ... after their panels were cleared (flat list of panel offsets)
+    template <class F> void map_sources(F code)
+    {
+        for (int &v : leaf_e_src) v = code(v);
+        for (int &v : leaf_piv_src) v = v >= 0 ? code(v) : v;
+        for (int &v : basm_src) v = code(v);
+        for (int &v : gasm_src) v = code(v);
+    }
 
     // Build from an upper-triangular CSC pattern (sorted rows, every diagonal entry present).
     // user_perm (may be null): caller-specified elimination order, like qdldl(A; perm=p) (qdldl.jl:134-136); it is

@@ -31,7 +31,7 @@ struct cb200_handle {
     const Symbolic &sym() const { return generic ? gsym : hp.sym; }
 };
 
-enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_TINV, X_LCSR, X_COUNT };
+enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_KX, X_LCSR, X_COUNT };
 
 extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
 extern "C" int cb200_device_count(void) { return 0; }
@@ -70,7 +70,7 @@ static Inst inst(cb200_handle *h, int b)
     I.g = at(CB200_EQUALITY); I.h = at(CB200_CONE);
     I.Wv = at(CB200_W_VALUES); I.Gv = at(CB200_G_VALUES); I.Cv = at(CB200_C_VALUES);
     I.prod = at(CB200_CONE_PRODUCT); I.bgrad = at(CB200_BARRIER_GRADIENT); I.lambda = at(CB200_DUAL);
-    I.panels = at(CB200_PANELS); I.D = at(CB200_PIVOTS); I.Dinv = at(X_DINV); I.Tinv = at(X_TINV); I.Lcsr = at(X_LCSR); I.prof = nullptr;
+    I.panels = at(CB200_PANELS); I.D = at(CB200_PIVOTS); I.Dinv = at(X_DINV); I.kx = at(X_KX); I.Lcsr = at(X_LCSR); I.prof = nullptr;
     I.xs = at(CB200_STEP_SYMMETRIC); I.rs = at(CB200_RESIDUAL_SYMMETRIC); I.xp = at(X_XP);
     I.mgrad = at(CB200_MERIT_GRADIENT); I.q = at(CB200_LQ_Q); I.g0 = at(CB200_LQ_G0); I.h0 = at(CB200_LQ_H0);
     I.filter = at(X_FILTER); I.krylov = h->ksize ? at(X_KRYLOV) : nullptr;
@@ -106,7 +106,7 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
     alloc(h, CB200_SCALARS, S_COUNT);
     for (int w : {(int)CB200_MERIT_GRADIENT, (int)CB200_RESIDUAL_SYMMETRIC, (int)CB200_STEP_SYMMETRIC, (int)CB200_PIVOTS, (int)X_DINV, (int)X_XP}) alloc(h, w, N);
     alloc(h, CB200_PANELS, P.panel_total);
-    alloc(h, X_TINV, P.tinv_total);
+    alloc(h, X_KX, P.kx_total);
     alloc(h, X_LCSR, P.lcsr_total);
     h->scratch.assign((size_t)h->hp.sym.scratch_doubles + 8, 0.0);
     alloc(h, X_FILTER, 4LL * h->opt.max_filter);
@@ -140,7 +140,7 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     for (int w : {(int)CB200_PIVOTS, (int)X_DINV, (int)X_XP, (int)CB200_RHS}) alloc(h, w, N);
     alloc(h, CB200_MATRIX_VALUES, Ap[N]);
     alloc(h, CB200_PANELS, h->P.panel_total);
-    alloc(h, X_TINV, h->P.tinv_total);
+    alloc(h, X_KX, h->P.kx_total);
     alloc(h, X_LCSR, h->P.lcsr_total);
     h->scratch.assign((size_t)h->gsym.scratch_doubles + 8, 0.0);
     h->istat.assign((size_t)batch * I_COUNT, 0);
@@ -268,8 +268,8 @@ extern "C" int cb200_apply_step(cb200_handle *h)
 extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves)
 {
     FOR_EACH_INSTANCE
-        kkt_assemble(ctx, P, I);
-        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, I.Tinv, I.Lcsr, I.istat, nullptr);
+        kkt_entries(ctx, P, I);
+        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, nullptr);
         for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
     END_FOR
     return 0;
@@ -321,9 +321,9 @@ extern "C" int cb200_ldl_factorize(cb200_handle *h)
     Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr};
     for (int b = 0; b < h->batch; b++) {
         double *pan = h->arr[CB200_PANELS].data() + (long long)b * h->P.panel_total;
-        matrix_assemble(ctx, h->P, pan, h->arr[CB200_MATRIX_VALUES].data() + (long long)b * h->P.nnzA);
+        const double *Ax = h->arr[CB200_MATRIX_VALUES].data() + (long long)b * h->P.nnzA;
         ldl_factor(ctx, h->P, pan, h->arr[CB200_PIVOTS].data() + (long long)b * h->P.N,
-                   h->arr[X_DINV].data() + (long long)b * h->P.N, h->arr[X_TINV].data() + (long long)b * h->P.tinv_total,
+                   h->arr[X_DINV].data() + (long long)b * h->P.N, KSrc{Ax, Ax, Ax, Ax},
                    h->arr[X_LCSR].data() + (long long)b * h->P.lcsr_total, h->istat.data() + (size_t)b * I_COUNT, nullptr);
     }
     return 0;
@@ -335,7 +335,7 @@ extern "C" int cb200_ldl_solve(cb200_handle *h)
         double *rhs = h->arr[CB200_RHS].data() + (long long)b * h->P.N;
         ldl_solve(ctx, h->P, h->arr[CB200_PANELS].data() + (long long)b * h->P.panel_total,
                   h->arr[CB200_PIVOTS].data() + (long long)b * h->P.N, h->arr[X_DINV].data() + (long long)b * h->P.N,
-                  h->arr[X_TINV].data() + (long long)b * h->P.tinv_total,
+                  h->arr[X_KX].data() + (long long)b * h->P.kx_total,
                   h->arr[X_LCSR].data() + (long long)b * h->P.lcsr_total, rhs, rhs,
                   h->arr[X_XP].data() + (long long)b * h->P.N, h->istat.data() + (size_t)b * I_COUNT, nullptr);
     }

@@ -11,8 +11,8 @@ extern "C" int symstats(int n, int m, int p, int q_nn, int nsoc, const int *soc_
     std::string msg = H.build(n, m, p, q_nn, nsoc, soc_dims, Wp, Wi, Gp, Gi, Cp, Ci, nullptr, big_threshold);
     if (!msg.empty()) { printf("error: %s\n", msg.c_str()); return -1; }
     const Symbolic &S = H.sym;
-    printf("N %d nnzK %d nnzL %lld flops(sum Lnz^2) %lld ns %d levels %d phases %zu panel_total %lld tinv_total %lld lcsr_total %lld scratch %d solve_smem %d nbig %zu\n",
-           S.N, S.nnzA, S.nnzL, S.flops, S.ns, S.nlevels, S.phases.size(), S.panel_total, S.tinv_total, S.lcsr_total,
+    printf("N %d nnzK %d nnzL %lld flops(sum Lnz^2) %lld ns %d levels %d phases %zu panel_total %lld kx_total %lld lcsr_total %lld scratch %d solve_smem %d nbig %zu\n",
+           S.N, S.nnzA, S.nnzL, S.flops, S.ns, S.nlevels, S.phases.size(), S.panel_total, S.kx_total, S.lcsr_total,
            S.scratch_doubles, S.solve_smem, S.big.size());
     long long leaf_cols = 0, leaf_rows = 0, big_cols = 0, small_cols = 0;
     std::map<int, int> leaf_hist;

@@ -40,8 +40,9 @@ STATUS_TEXT = {0: "ok", 1: "inertia correction failure", 2: "iterative refinemen
 
 PROFILE = ["assemble", "factor_leaves", "factor_small", "factor_big_stage", "factor_big_gemm", "factor_big_panel",
            "factor_big_generic", "solve_fwd", "solve_bwd", "rhs_recover", "jtimes", "eval_linesearch", "cone_residual",
-           "inertia", "total"]
-PROF_COUNT = 16
+           "inertia", "total", "sf_bulk", "sf_pull", "sf_sweep", "sf_push", "sf_other", "sb_gather", "sb_sweep", "sb_other",
+           "sb_leaves"]
+PROF_COUNT = 24
 
 EV_OBJECTIVE, EV_GRADIENT, EV_EQUALITY, EV_CONE, EV_EQUALITY_DUAL_GRAD, EV_CONE_DUAL_GRAD = 1, 2, 4, 8, 16, 32
 EV_HESSIAN, EV_EQUALITY_JAC, EV_CONE_JAC = 64, 128, 256

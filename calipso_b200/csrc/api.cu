@@ -15,6 +15,13 @@
 
 using namespace cb200;
 
+// phase counters: shared-memory accumulators -> the instance's slots (only when profiling is on)
+#define PROF_FLUSH(ptr)                                                                  \
+    do {                                                                                 \
+        __syncthreads();                                                                 \
+        if ((ptr) && threadIdx.x < PROF_COUNT) (ptr)[threadIdx.x] += cb_prof[threadIdx.x]; \
+    } while (0)
+
 static_assert(sizeof(cb200_options) == sizeof(Options), "cb200_options must mirror cb200::Options");
 static_assert((int)CB200_S_COUNT == (int)S_COUNT && (int)CB200_I_COUNT == (int)I_COUNT, "slot enums out of sync");
 
@@ -56,6 +63,7 @@ struct Batch {
 #define CB_THREADS 256
 #define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
 #define CTX_SETUP                                                                                          \
+    if (threadIdx.x < 32) cb_prof[threadIdx.x] = 0;                                                        \
     if (threadIdx.x == 0) {                                                                                \
         mbar_init(&cb_bars[0], 1);                                                                         \
         mbar_init(&cb_bars[1], 1);                                                                         \
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_search_direction(co
     KERNEL_PROLOGUE
     int st = search_direction(ctx, P, I, o);
     if (ctx.tid == 0) I.istat[I_STATUS] = st;
+    PROF_FLUSH(I.prof);
 }
 
 __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_cone_search(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_step(const __gri
 {
     KERNEL_PROLOGUE
     solve_step_lq(ctx, P, I, o);
+    PROF_FLUSH(I.prof);
 }
 
 // LinearSolver seam: factor the generic matrix / solve in place.  These two are the "KKT LDL^T solve" whose HBM
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_factor(const __
     (void)assemble_generic;
     const double *Ax = B.Aval + b * (long long)P.nnzA;
     ldl_factor(ctx, P, pan, D, Dinv, KSrc{Ax, Ax, Ax, Ax}, B.Lcsr + b * P.lcsr_total, istat, B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
+    PROF_FLUSH(B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
 __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
@@ -167,6 +178,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __g
     ldl_solve(ctx, P, B.panels + b * P.panel_total, B.D + b * (long long)P.N, B.Dinv + b * (long long)P.N,
               B.kx + b * P.kx_total, B.Lcsr + b * P.lcsr_total, rhs, rhs, B.xp + b * (long long)P.N, B.istat + b * (long long)I_COUNT,
               B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
+    PROF_FLUSH(B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
 // KKT path: assemble + factor with the current regularisation (no inertia loop) -- used by the roofline bench
@@ -179,6 +191,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(co
     pt.stop(PROF_ASSEMBLE);
     ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
     for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
+    PROF_FLUSH(I.prof);
 }
 
 __global__ void k_count_states(Batch B, long long *counts)

@@ -81,6 +81,8 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     long long kx_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
     int nbig, max_sb_doubles, solve_smem;
+    const int *parts_fwd, *parts_bwd;          // (panel offset, doubles) of the TMA copies of the solves, in issue order
+    int nparts_fwd, nparts_bwd;
     // assembly destinations (offsets into the panel storage)
     const long long *dW, *dG, *dC, *dY, *dZnn, *dZsoc;
     const long long *dA;                       // generic-matrix mode (LinearSolver seam): one per input entry
@@ -108,7 +110,10 @@ struct Options {      // src/solver/options.jl:6-59, hot-path subset (same defau
 enum {
     PROF_ASSEMBLE = 0, PROF_FACTOR_LEAVES, PROF_FACTOR_SMALL, PROF_FACTOR_BIG_STAGE, PROF_FACTOR_BIG_GEMM,
     PROF_FACTOR_BIG_PANEL, PROF_FACTOR_BIG_GENERIC, PROF_SOLVE_FWD, PROF_SOLVE_BWD, PROF_RHS_RECOVER, PROF_JTIMES,
-    PROF_EVAL_LINESEARCH, PROF_CONE_RESIDUAL, PROF_INERTIA, PROF_TOTAL, PROF_COUNT = 16
+    PROF_EVAL_LINESEARCH, PROF_CONE_RESIDUAL, PROF_INERTIA, PROF_TOTAL,
+    // sub-phases of the shared-memory solve
+    PROF_SF_BULK, PROF_SF_PULL, PROF_SF_SWEEP, PROF_SF_PUSH, PROF_SF_OTHER, PROF_SB_GATHER, PROF_SB_SWEEP, PROF_SB_OTHER,
+    PROF_SB_LEAVES, PROF_COUNT = 24
 };
 
 // per-instance scalar slots
@@ -180,6 +185,7 @@ extern __shared__ __align__(16) double cb_dyn_smem[];
 __shared__ double cb_red[34];
 __shared__ __align__(8) unsigned long long cb_bars[2];
 __shared__ unsigned cb_bar_uses;
+__shared__ long long cb_prof[32];      // phase counters of this CTA, flushed to the instance's slots when the kernel ends
 #define CB_SCRATCH(ctx) (cb_dyn_smem)
 #define CB_RED(ctx) (cb_red)
 #else
@@ -469,7 +475,7 @@ struct ProfTimer {       // thread 0 of the CTA accumulates clock64() deltas int
     CB_DEV void stop(int slot)
     {
 #if CB_ON_DEVICE
-        if (slots && threadIdx.x == 0) { long long t1 = clock64(); slots[slot] += t1 - t0; t0 = t1; }
+        if (slots && threadIdx.x == 0) { long long t1 = clock64(); cb_prof[slot] += t1 - t0; t0 = t1; }
 #endif
     }
 };
@@ -796,26 +802,20 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
                 if (ti >= tj && m) {
                     const double *ya = Y + 8 * ti + gid + tig * ldy, *yb = Y + 8 * tj + gid + tig * ldy;
                     const double *dy = Dy + tig;
+                    // dense loop over the span of column groups present in both tile rows (block-structured sparsity:
+                    // the span is tight); regular addressing, two accumulators
+                    const int g0 = __ffs(m) - 1, g1 = 32 - __clz(m);
+                    ya += 4 * g0 * ldy; yb += 4 * g0 * ldy; dy += 4 * g0;
                     double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-                    while (m) {      // four column groups per round: twelve shared-memory loads in flight
-                        int g[4];
-                        double av[4], bv[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            g[u] = m ? __ffs(m) - 1 : -1;
-                            m &= m - 1;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int go = 4 * max(g[u], 0);
-                            av[u] = ya[go * ldy];
-                            bv[u] = g[u] >= 0 ? yb[go * ldy] * dy[go] : 0.0;
-                        }
-                        dmma_8x8x4(e0, e1, av[0], bv[0]);
-                        dmma_8x8x4(f0, f1, av[1], bv[1]);
-                        dmma_8x8x4(e0, e1, av[2], bv[2]);
-                        dmma_8x8x4(f0, f1, av[3], bv[3]);
+                    int g = g0;
+#pragma unroll 2
+                    for (; g + 1 < g1; g += 2) {
+                        const double a0 = ya[0], b0 = yb[0] * dy[0], a1 = ya[4 * ldy], b1 = yb[4 * ldy] * dy[4];
+                        dmma_8x8x4(e0, e1, a0, b0);
+                        dmma_8x8x4(f0, f1, a1, b1);
+                        ya += 8 * ldy; yb += 8 * ldy; dy += 8;
                     }
+                    if (g < g1) dmma_8x8x4(e0, e1, ya[0], yb[0] * dy[0]);
                     const int r = 8 * ti + gid, col = 8 * tj + 2 * tig;
                     if (r < nrow) {
                         if (col < w) S[r + col * ldp] -= e0 + f0;
@@ -849,10 +849,11 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
         PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
         ctx.sync();
     }
-    // write back the factor panel (pivots on the diagonal)
+    // write back the factor panel; the diagonal and the upper triangle of the pivot block are stored as zeros so
+    // that the triangular sweeps of the solves need no predicates
     for (int k = wid; k < w; k += nw) {
         const double *src = S + k * ldp;
-        for (int i = lane; i < nrow; i += 32) Ps[i + k * nrow] = i == k ? dd[k] : src[i];
+        for (int i = lane; i < nrow; i += 32) Ps[i + k * nrow] = i <= k ? 0.0 : src[i];   // strictly lower part only
     }
 #else
     panel_factor(ctx, S, nrow, w, ldp);
@@ -860,7 +861,7 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
     ctx.sync();
     PAR_FOR(e, nrow * w) {
         int k = e / nrow, i = e % nrow;
-        Ps[e] = i == k ? dd[k] : S[i + (long long)k * ldp];
+        Ps[e] = i <= k ? 0.0 : S[i + (long long)k * ldp];
     }
 #endif
     PAR_FOR(k, w) {
@@ -986,48 +987,56 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
 
 
 #if CB_ON_DEVICE
-// Fast path of ldl_solve (same arithmetic).  The permuted vector lives in global memory (xp: 8N bytes, L1/L2
-// resident); the chain of shared-memory supernodes streams its factor panels through two shared-memory buffers filled
-// by TMA bulk copies one supernode ahead (mbarrier complete_tx), so no global-memory latency sits on the critical
-// path of the elimination-tree chain.  Per chain supernode: the w x w unit-triangular block is solved by ONE warp with
-// register-resident unknowns and shuffles (no CTA barrier per pivot), the rectangular part L_R is a mat-vec spread
-// over the whole CTA (four threads per row / column, shuffle-reduced).  Singleton leaves are handled in bulk by
-// eight-lane groups (coalesced).  Work area: buf0 | buf1 | y[64].
+// Fast path of ldl_solve (same arithmetic).  The permuted vector lives in shared memory for the whole solve; the chain
+// of shared-memory supernodes streams its factor panels, in one or two column parts, through two shared-memory
+// buffers filled by TMA bulk copies one part ahead (mbarrier complete_tx), so no global-memory latency sits on the
+// critical path of the elimination-tree chain.  Per chain supernode: the w x w unit-triangular block is solved by ONE
+// warp with register-resident unknowns and shuffles (no CTA barrier per pivot), the rectangular part L_R is a mat-vec
+// spread over the whole CTA (four threads per row / column, shuffle-reduced).  Singleton leaves are handled in bulk
+// by four-lane groups (coalesced).  Work area: x[N] | part buffer 0 | part buffer 1 | y[64].
 __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P, const double *__restrict__ pan,
                                             const double *D, const double *__restrict__ Dinv,
-                                            const double *__restrict__ Lcsr, const double *b, double *x, double *xp,
+                                            const double *__restrict__ Lcsr, const double *b, double *x,
                                             int *istat, long long *prof)
 {
-    ProfTimer pt{prof, 0};
+    ProfTimer pt{prof, 0}, ps{prof, 0};
     pt.start();
-    const int N = P.N;
+    ps.start();
+    const int N = P.N, Npad = (N + 1) & ~1;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    double *buf[2] = {cb_dyn_smem, cb_dyn_smem + P.max_sb_doubles};
-    double *yv = buf[1] + P.max_sb_doubles;
+    double *xs = cb_dyn_smem;
+    const int buf_off = Npad, buf_len = P.max_sb_doubles;      // part buffer `slot` at cb_dyn_smem + buf_off + slot * buf_len
+    double *yv = cb_dyn_smem + buf_off + 2 * buf_len;            // (named from cb_dyn_smem so that accesses stay LDS/STS)
+    double *zero_cell = yv + 64;
     unsigned long long *bars = cb_bars;
-    for (int k = tid; k < N; k += nthr) xp[k] = b[P.perm[k]];
+    if (tid == 0) *zero_cell = 0.0;
+    for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
     // the barriers live for the whole kernel: continue the issue/consume numbering where the previous solve stopped
     unsigned issued = cb_bar_uses, consumed = issued;
-    const int *seq = P.big_seq;
-    auto issue = [&](int seq_idx) {    // called by all threads after a CTA barrier; thread 0 launches the copy
-        if (tid == 0) {
-            const int sn = seq[seq_idx];
-            const unsigned bytes = (unsigned)P.big[P.big_index[sn]].panel_doubles * 8u;
-            const int slot = issued & 1;
-            fence_proxy_async();
-            mbar_expect_tx(&bars[slot], bytes);
-            tma_bulk_g2s(buf[slot], pan + P.panel_off[sn], bytes, &bars[slot]);
+    const int *parts = P.parts_fwd;
+    int nparts = P.nparts_fwd, next_part = 0;
+    auto issue = [&]() {    // called by all threads after a CTA barrier that freed the slot; thread 0 launches the copy
+        if (next_part < nparts) {
+            if (tid == 0) {
+                const int off = parts[2 * next_part];
+                const unsigned bytes = (unsigned)parts[2 * next_part + 1] * 8u;
+                const int slot = issued & 1;
+                fence_proxy_async();
+                mbar_expect_tx(&bars[slot], bytes);
+                tma_bulk_g2s(cb_dyn_smem + buf_off + slot * buf_len, pan + off, bytes, &bars[slot]);
+            }
+            issued++;
+            next_part++;
         }
-        issued++;
     };
-    auto acquire = [&]() -> const double * {
+    auto acquire = [&]() -> int {       // returns the slot that holds the part
         const int slot = consumed & 1;
         mbar_wait(&bars[slot], (unsigned)((consumed >> 1) & 1));
         consumed++;
-        return buf[slot];
+        return slot;
     };
     __syncthreads();
-    if (P.nbig > 0) issue(0);
+    issue();
     // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final);
     // four lanes per column, columns without leaf descendants are not visited
     {
@@ -1038,13 +1047,13 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             [&](int r, int sub, int st) {
                 const int4 ri = info[r];
                 double acc = 0.0;
-                for (int q = ri.y + sub; q < ri.z; q += st) acc += Lcsr[q] * xp[lcol[q]];
+                for (int q = ri.y + sub; q < ri.z; q += st) acc += Lcsr[q] * xs[lcol[q]];
                 return acc;
             },
-            [&](int r, double acc) { xp[info[r].x] -= acc; });
+            [&](int r, double acc) { xs[info[r].x] -= acc; });
     }
     __syncthreads();
-    int pos = 0;
+    ps.stop(PROF_SF_BULK);
     for_each_supernode(
         ctx, P, true,
         [&](const Ctx &c, int s) {
@@ -1053,50 +1062,65 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
             const int bi = c.warp_scope ? -1 : P.big_index[s];
             if (bi >= 0) {
+                const int h1 = P.big[bi].h1;
+                const int *__restrict__ R = P.rows + P.rows_ptr[s];
                 if (tid < w) {   // pull from small (non-leaf, non-shared-memory) descendants
                     double acc = 0.0;
                     for (int q = P.fwd_ptr[c0 + tid]; q < P.fwd_ptr[c0 + tid + 1]; q++) {
                         const FwdEntry fe = P.fwd[q];
                         const double *Ld = pan + fe.off;
-                        for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
+                        for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
                     }
-                    yv[tid] = xp[c0 + tid] - acc;
-                }
-                if (pos + 1 < P.nbig) issue(pos + 1);
-                const double *L = acquire();
-                pos++;
-                __syncthreads();
-                if (wid == 0) {      // L_tt y = v, unit lower triangular, unknowns in registers (w <= 64)
-                    double y0 = lane < w ? yv[lane] : 0.0, y1 = lane + 32 < w ? yv[lane + 32] : 0.0;
-#pragma unroll 4
-                    for (int k = 0; k < w - 1; k++) {
-                        const double l0 = (lane > k && lane < w) ? L[lane + k * nrow] : 0.0;
-                        const double l1 = (lane + 32 > k && lane + 32 < w) ? L[lane + 32 + k * nrow] : 0.0;
-                        const double yk = __shfl_sync(0xffffffffu, k < 32 ? y0 : y1, k & 31);
-                        y0 -= l0 * yk;
-                        y1 -= l1 * yk;
-                    }
-                    if (lane < w) { yv[lane] = y0; xp[c0 + lane] = y0; }
-                    if (lane + 32 < w) { yv[lane + 32] = y1; xp[c0 + lane + 32] = y1; }
+                    yv[tid] = xs[c0 + tid] - acc;
                 }
                 __syncthreads();
-                {   // push x[R] -= L_R y, four threads per row
-                    const int *__restrict__ R = P.rows + P.rows_ptr[s];
-                    const int part = tid & 3;
-                    for (int base = 0; base < nR; base += nthr >> 2) {
-                        const int i = base + (tid >> 2);
-                        double acc = 0.0;
-                        if (i < nR) {
-                            const double *Lr = L + w + i;
+                double y0 = 0.0, y1 = 0.0;      // warp 0: unknowns lane, lane + 32 (w <= 64)
+                if (wid == 0) { y0 = lane < w ? yv[lane] : 0.0; y1 = lane + 32 < w ? yv[lane + 32] : 0.0; }
+                for (int k0 = 0; k0 < w; k0 = (k0 == 0 ? h1 : w)) {
+                    const int k1 = k0 == 0 ? h1 : w;
+                    issue();                                  // the slot of the previous part is free (barrier above / below)
+                    const double *L = cb_dyn_smem + (buf_off + acquire() * buf_len - k0 * nrow);  // column k of the panel at L + k * nrow
+                        if (wid == 0) {      // L_tt y = v, unit lower triangular (zeros stored on and above the diagonal)
+                        const double *Lk0 = L + k0 * nrow + min(lane, nrow - 1), *Lk1 = L + k0 * nrow + min(lane + 32, nrow - 1);
+                        const int ka = min(k1, 32);
+                        int k = k0;
 #pragma unroll 4
-                            for (int k = part; k < w; k += 4) acc += Lr[k * nrow] * yv[k];
+                        for (; k < ka; k++) {
+                            const double l0 = *Lk0, l1 = *Lk1;
+                            const double yk = __shfl_sync(0xffffffffu, y0, k);
+                            y0 -= l0 * yk;
+                            y1 -= l1 * yk;
+                            Lk0 += nrow; Lk1 += nrow;
                         }
-                        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                        if (part == 0 && i < nR) xp[R[i]] -= acc;
+#pragma unroll 4
+                        for (; k < k1; k++) {     // pivots 32 .. 63 live in y1 and only touch y1
+                            const double l1 = *Lk1;
+                            const double yk = __shfl_sync(0xffffffffu, y1, k - 32);
+                            y1 -= l1 * yk;
+                            Lk1 += nrow;
+                        }
+                        // y[k0 .. k1) are final
+                        if (lane >= k0 && lane < k1) { yv[lane] = y0; xs[c0 + lane] = y0; }
+                        if (lane + 32 >= k0 && lane + 32 < k1) { yv[lane + 32] = y1; xs[c0 + lane + 32] = y1; }
                     }
-                }
-                __syncthreads();
+                        __syncthreads();
+                    {   // push x[R] -= L_R[:, k0:k1) y[k0:k1), four threads per row
+                        const int part = tid & 3;
+                        for (int base = 0; base < nR; base += nthr >> 2) {
+                            const int i = base + (tid >> 2);
+                            double acc = 0.0;
+                            if (i < nR) {
+                                const double *Lr = L + w + i;
+#pragma unroll 4
+                                for (int k = k0 + part; k < k1; k += 4) acc += Lr[k * nrow] * yv[k];
+                            }
+                            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                            if (part == 0 && i < nR) xs[R[i]] -= acc;
+                        }
+                    }
+                    __syncthreads();
+                    }
                 return;
             }
             PAR_FOR(j, w) {   // pull from small (non-leaf, non-shared-memory) descendants
@@ -1104,25 +1128,26 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                 for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
                     const FwdEntry fe = P.fwd[q];
                     const double *Ld = pan + fe.off;
-                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xp[fe.col0 + k];
+                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
                 }
-                if (acc != 0.0) xp[c0 + j] -= acc;
+                if (acc != 0.0) xs[c0 + j] -= acc;
             }
             const double *Ps = pan + P.panel_off[s];
             for (int k = 0; k + 1 < w; k++) {
                 ctx.sync();
-                const double xk = xp[c0 + k];
-                PAR_FOR(i, w - 1 - k) xp[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
+                const double xk = xs[c0 + k];
+                PAR_FOR(i, w - 1 - k) xs[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
             }
             ctx.sync();
         },
         [&](const Ctx &, int, int, int, int) {});
-    for (int k = tid; k < N; k += nthr) xp[k] *= Dinv[k];
+    for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
-    pos = 0;
-    seq = P.big_seq_bwd;
-    if (P.nbig > 0) issue(0);
+    parts = P.parts_bwd;
+    nparts = P.nparts_bwd;
+    next_part = 0;
+    issue();
     for_each_supernode(
         ctx, P, false,
         [&](const Ctx &c, int s) {
@@ -1132,56 +1157,78 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             const int *__restrict__ R = P.rows + P.rows_ptr[s];
             const int bi = c.warp_scope ? -1 : P.big_index[s];
             if (bi >= 0) {
-                if (pos + 1 < P.nbig) issue(pos + 1);
-                const double *L = acquire();
-                pos++;
-                {   // v_k = x_k - sum_i L_R[i, k] x[R_i], four threads per column
-                    const int part = tid & 3;
-                    for (int base = 0; base < w; base += nthr >> 2) {
-                        const int k = base + (tid >> 2);
-                        double acc = 0.0;
-                        if (k < w) {
-                            const double *Lc = L + w + k * nrow;
+                const int h1 = P.big[bi].h1;
+                double z0 = 0.0, z1 = 0.0;      // warp 0: unknowns lane, lane + 32
+                if (wid == 0) { z0 = lane < w ? xs[c0 + lane] : 0.0; z1 = lane + 32 < w ? xs[c0 + lane + 32] : 0.0; }
+                for (int k1 = w; k1 > 0; k1 = (k1 == w && h1 < w ? h1 : 0)) {     // column parts in reverse order
+                    const int k0 = (k1 == w && h1 < w) ? h1 : 0;
+                    issue();
+                    const double *L = cb_dyn_smem + (buf_off + acquire() * buf_len - k0 * nrow);
+                    {   // t_k = sum_{r >= k1} L[r, k] x_r for the columns k in [k0, k1) of this part: rows k1 .. w-1 are the
+                        // pivots of the part solved before (final in xs), rows w .. are R; four threads per column
+                        const int part = tid & 3;
+                        for (int base = k0; base < k1; base += nthr >> 2) {
+                            const int k = base + (tid >> 2);
+                            double acc = 0.0;
+                            if (k < k1) {
+                                const double *Lc = L + k * nrow;
 #pragma unroll 4
-                            for (int i = part; i < nR; i += 4) acc += Lc[i] * xp[R[i]];
+                                for (int r = k1 + part; r < nrow; r += 4) acc += Lc[r] * (r < w ? xs[c0 + r] : xs[R[r - w]]);
+                            }
+                            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                            if (part == 0 && k < k1) yv[k] = acc;
                         }
-                        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                        if (part == 0 && k < w) yv[k] = xp[c0 + k] - acc;
                     }
-                }
-                __syncthreads();
-                if (wid == 0) {      // L_tt' z = v, unit upper triangular
-                    double z0 = lane < w ? yv[lane] : 0.0, z1 = lane + 32 < w ? yv[lane + 32] : 0.0;
+                    __syncthreads();
+                        if (wid == 0) {      // L_tt' z = v restricted to the part: unit upper triangular, columns k1-1 .. k0
+                        if (lane >= k0 && lane < k1) z0 -= yv[lane];
+                        if (lane + 32 >= k0 && lane + 32 < k1) z1 -= yv[lane + 32];
+                        // row k of the block: column `lane` (zeros on and above the diagonal); lanes whose column is not
+                        // in this part read a zero cell with stride 0
+                        const bool in0 = lane >= k0 && lane < k1, in1 = lane + 32 >= k0 && lane + 32 < k1;
+                        const double *p0 = in0 ? L + lane * nrow + (k1 - 1) : zero_cell;
+                        const double *p1 = in1 ? L + (lane + 32) * nrow + (k1 - 1) : zero_cell;
+                        const int s0 = in0 ? 1 : 0, s1 = in1 ? 1 : 0;
+                        int k = k1 - 1;
 #pragma unroll 4
-                    for (int k = w - 1; k > 0; k--) {
-                        const double l0 = lane < k ? L[k + lane * nrow] : 0.0;
-                        const double l1 = lane + 32 < k ? L[k + (lane + 32) * nrow] : 0.0;
-                        const double zk = __shfl_sync(0xffffffffu, k < 32 ? z0 : z1, k & 31);
-                        z0 -= l0 * zk;
-                        z1 -= l1 * zk;
+                        for (; k > k0 && k >= 32; k--) {
+                            const double l0 = *p0, l1 = *p1;
+                            const double zk = __shfl_sync(0xffffffffu, z1, k - 32);
+                            z0 -= l0 * zk;
+                            z1 -= l1 * zk;
+                            p0 -= s0; p1 -= s1;
+                        }
+#pragma unroll 4
+                        for (; k > k0; k--) {     // pivots below 32 only touch z0
+                            const double l0 = *p0;
+                            const double zk = __shfl_sync(0xffffffffu, z0, k);
+                            z0 -= l0 * zk;
+                            p0 -= s0;
+                        }
+                        if (lane >= k0 && lane < k1) xs[c0 + lane] = z0;
+                        if (lane + 32 >= k0 && lane + 32 < k1) xs[c0 + lane + 32] = z1;
                     }
-                    if (lane < w) xp[c0 + lane] = z0;
-                    if (lane + 32 < w) xp[c0 + lane + 32] = z1;
+                        __syncthreads();
                 }
-                __syncthreads();
                 return;
             }
             const double *Ps = pan + P.panel_off[s];
             PAR_FOR(k, w) {
                 double acc = 0.0;
                 const double *col = Ps + (long long)k * nrow + w;
-                for (int i = 0; i < nR; i++) acc += col[i] * xp[R[i]];
-                xp[c0 + k] -= acc;
+                for (int i = 0; i < nR; i++) acc += col[i] * xs[R[i]];
+                xs[c0 + k] -= acc;
             }
             for (int k = w - 1; k > 0; k--) {
                 ctx.sync();
-                const double xk = xp[c0 + k];
-                PAR_FOR(i, k) xp[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
+                const double xk = xs[c0 + k];
+                PAR_FOR(i, k) xs[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
             }
             ctx.sync();
         },
         [&](const Ctx &c, int begin, int end, int, int) {   // singleton leaves: four lanes per leaf
+            ps.stop(PROF_SB_OTHER);
             const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.leaf_info) + begin;
             const int *__restrict__ rows = P.rows;
             grouped_rows<4>(
@@ -1191,13 +1238,14 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                     const double *__restrict__ col = pan + li.z;
                     const int *__restrict__ R = rows + li.w;
                     double acc = 0.0;
-                    for (int i = sub; i < li.y; i += st) acc += col[i] * xp[R[i]];
+                    for (int i = sub; i < li.y; i += st) acc += col[i] * xs[R[i]];
                     return acc;
                 },
-                [&](int q, double acc) { xp[info[q].x] -= acc; });
+                [&](int q, double acc) { xs[info[q].x] -= acc; });
             __syncthreads();
+            ps.stop(PROF_SB_LEAVES);
         });
-    for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xp[k];
+    for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
     if (tid == 0 && istat) istat[I_SOLVES]++;
     __syncthreads();
     if (tid == 0) cb_bar_uses = issued;
@@ -1215,7 +1263,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
 {
 #if CB_ON_DEVICE
     if (P.solve_smem && ctx.scratch && blockDim.x >= 128) {
-        ldl_solve_smem(ctx, P, pan, D, Dinv, Lcsr, b, x, xp, istat, prof);
+        ldl_solve_smem(ctx, P, pan, D, Dinv, Lcsr, b, x, istat, prof);
         return;
     }
 #endif

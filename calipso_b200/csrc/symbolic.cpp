@@ -396,6 +396,8 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             bt.ldp = ldp;
             bt.panel_doubles = (int)(panel_off[t + 1] - panel_off[t]);
             bt.asm_begin = bt.asm_end = 0;
+            bt.h1 = w;
+            if (bt.panel_doubles > 2048 && w >= 4) bt.h1 = ((w + 1) / 2 + 1) & ~1;   // even => both parts 16-byte aligned
             int col = 0;
             YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
             ymask.resize(ymask.size() + ntI, 0u);
@@ -436,7 +438,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             big_index[t] = (int)big.size();
             big.push_back(bt);
             big_seq.push_back(t);
-            max_sb_doubles = std::max(max_sb_doubles, bt.panel_doubles);
+            max_sb_doubles = std::max(max_sb_doubles, std::max(nrow * bt.h1, bt.panel_doubles - nrow * bt.h1));
             const long long ysize = (long long)((max_kc + 3) & ~3) * (ldy + 1);
             scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>(ysize, aux) + 8);
         }
@@ -446,10 +448,23 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         if (phases[pi].mode == 1)
             for (int q = phases[pi].begin; q < phases[pi].end; q++)
                 if (big_index[order[q]] >= 0) big_seq_bwd.push_back(order[q]);
-    {   // shared-memory solve: two panel buffers (TMA double buffering) + the pivot / row windows of the vector
-        long long need = 2LL * max_sb_doubles + 4 * 64 + 16;
+    {   // shared-memory solve: the permuted vector, two part buffers (TMA double buffering), one pivot window
+        max_sb_doubles = (max_sb_doubles + 1) & ~1;
+        long long need = (((long long)N + 1) & ~1LL) + 2LL * max_sb_doubles + 64 + 16;
         solve_smem = (!big.empty() && need <= smem_budget_doubles) ? 1 : 0;
         if (solve_smem) scratch_doubles = (int)std::max<long long>(scratch_doubles, need);
+        parts_fwd.clear(); parts_bwd.clear();
+        auto parts_of = [&](int t, bool forward, std::vector<int> &out) {
+            const BigTarget &bt = big[big_index[t]];
+            const int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
+            const int off0 = (int)panel_off[t], len0 = bt.h1 == w ? bt.panel_doubles : nrow * bt.h1;
+            const int off1 = off0 + len0, len1 = bt.panel_doubles - len0;
+            if (bt.h1 == w) { out.push_back(off0); out.push_back(len0); }
+            else if (forward) { out.insert(out.end(), {off0, len0, off1, len1}); }
+            else { out.insert(out.end(), {off1, len1, off0, len0}); }
+        };
+        for (int t : big_seq) parts_of(t, true, parts_fwd);
+        for (int t : big_seq_bwd) parts_of(t, false, parts_bwd);
     }
     // 6c. forward-solve row lists (row c of L, grouped by the supernode that stores it); singleton leaves apart,
     //     shared-memory (big) supernodes excluded: they push

@@ -42,6 +42,7 @@ struct BigTarget {
     int ldp;                     // leading dimension of the panel work area (same rounding)
     int panel_doubles;           // size of the supernode's panel in the factor storage (even): one TMA bulk copy in the solves
     int asm_begin, asm_end;      // range in basm_src / basm_dst: the input entries of this supernode (fused assembly)
+    int h1;                      // the solves stream the panel in one part (h1 == w) or two: columns [0, h1) and [h1, w)
 };
 struct FwdEntry {                // one (descendant, row) pair of the forward-solve row lists, flattened
     int off;                     // panel offset of L_d[row, 0]
@@ -99,7 +100,8 @@ struct Symbolic {
     std::vector<unsigned> ymask;
     std::vector<int> big_seq;     // shared-memory supernodes in forward schedule order (TMA prefetch chain)
     std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
-    int max_sb_doubles = 0;       // largest panel of a shared-memory supernode
+    std::vector<int> parts_fwd, parts_bwd;   // TMA copies of the solves in issue order: (panel offset, doubles) pairs
+    int max_sb_doubles = 0;       // largest part (see BigTarget::h1) of a shared-memory supernode's panel
     int solve_smem = 0;           // 1: x and two solve-block buffers fit in the CTA work area (ldl_solve fast path)
     long long kx_total = 0;     // (unused: the solves read the factor panels directly)
     int scratch_doubles = 0;      // shared-memory doubles a CTA needs

@@ -142,7 +142,7 @@ int cb200_set_array(cb200_handle *h, int which, const double *host, int first_in
 int cb200_get_array(cb200_handle *h, int which, double *host, int first_instance, int count);       /* D2H + sync */
 int cb200_get_stats(cb200_handle *h, int *host /* [count][CB200_I_COUNT] */, int first_instance, int count);
 int cb200_array_length(const cb200_handle *h, int which);
-/* per-instance cycle counters of the factor/solve phases, [batch][16] (thread 0 of each CTA, clock64); reset != 0
+/* per-instance cycle counters of the factor/solve phases, [batch][24] (thread 0 of each CTA, clock64); reset != 0
  * zeroes them afterwards.  Diagnostic only: the counters are off until this function is called for the first time
  * (that call returns zeros) because they cost a global read-modify-write per phase. */
 int cb200_get_profile(cb200_handle *h, long long *host, int reset);

@@ -1,0 +1,52 @@
+"""The drop-in boundary: libcalipso_b200.so loads without a GPU and exports every symbol include/calipso_b200.h declares
+(no compute calls here); the Python binding table covers the same set; the test-only emulation exports it too."""
+import ctypes
+import os
+import re
+
+import backends
+from calipso_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "calipso_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_path():
+    names = declared_symbols()
+    for must in ("cb200_create", "cb200_ldl_create", "cb200_residual", "cb200_search_direction", "cb200_cone",
+                 "cb200_cone_search", "cb200_apply_step", "cb200_ldl_factorize", "cb200_ldl_inertia", "cb200_ldl_solve",
+                 "cb200_ldl_linear_solve", "cb200_allreduce_counts"):
+        assert must in names
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(build.build())
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header():
+    assert sorted(_lib.SYMBOLS) == declared_symbols()
+
+
+def test_emulation_exports_the_same_boundary():
+    lib = backends.binding("emul").lib
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_a_device():
+    """cb200_create must fail loudly (not fall back) when there is no CUDA device."""
+    b = _lib.Binding(build.build())
+    if b.lib.cb200_device_count() > 0:
+        return
+    from calipso_b200 import lqc
+    from calipso_b200.solver import BatchKKT
+    import pytest
+    with pytest.raises(Exception, match="no CUDA device"):
+        BatchKKT(lqc.tiny(), binding=b)

@@ -81,6 +81,9 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     long long kx_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
     int nbig, max_sb_doubles, solve_smem;
+    const FwdEntry *pfwd;                      // per-phase bulk pulls into the pivot columns of the shared-memory supernodes
+    const int *prow, *pphase_ptr;
+    int max_big_nR;
     const int *parts_fwd, *parts_bwd;          // (panel offset, doubles) of the TMA copies of the solves, in issue order
     int nparts_fwd, nparts_bwd;
     // assembly destinations (offsets into the panel storage)
@@ -885,7 +888,8 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
 
 // Run the level schedule (forward = leaves first): f(scope, supernode) for warp-/CTA-scope supernodes and
 // g(cta, begin, end) for a phase of singleton leaves (range in P.order).
-template <class F, class G> CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward, F f, G g)
+template <class F, class G, class E>
+CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward, F f, G g, E phase_end)
 {
     Ctx wctx = cta;
 #if CB_ON_DEVICE
@@ -903,7 +907,12 @@ template <class F, class G> CB_DEV void for_each_supernode(const Ctx &cta, const
             for (int q = ph.begin + CB_WARP_ID; q < ph.end; q += CB_NUM_WARPS) f(wctx, P.order[q]);
         }
         CB_CTA_SYNC();
+        phase_end(forward ? pi : P.nphases - 1 - pi, ph.mode);
     }
+}
+template <class F, class G> CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward, F f, G g)
+{
+    for_each_supernode(cta, P, forward, f, g, [](int, int) {});
 }
 
 // numeric factorisation + inertia (positive = #(D>0), negative = #(D<=0), zero = #(D==0); linear_solver.jl:33-44)
@@ -1008,6 +1017,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     const int buf_off = Npad, buf_len = P.max_sb_doubles;      // part buffer `slot` at cb_dyn_smem + buf_off + slot * buf_len
     double *yv = cb_dyn_smem + buf_off + 2 * buf_len;            // (named from cb_dyn_smem so that accesses stay LDS/STS)
     double *zero_cell = yv + 64;
+    double *xr = yv + 80;                                         // x[R] of the current chain supernode (backward)
     unsigned long long *bars = cb_bars;
     if (tid == 0) *zero_cell = 0.0;
     for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
@@ -1042,15 +1052,31 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     {
         const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.lcsr_rowinfo);
         const int *__restrict__ lcol = P.lcsr_col;
-        grouped_rows<4>(
-            ctx, P.lcsr_ncols,
-            [&](int r, int sub, int st) {
-                const int4 ri = info[r];
-                double acc = 0.0;
-                for (int q = ri.y + sub; q < ri.z; q += st) acc += Lcsr[q] * xs[lcol[q]];
-                return acc;
-            },
-            [&](int r, double acc) { xs[info[r].x] -= acc; });
+        const int sub = tid & 3, grp = tid >> 2, ngrp = nthr >> 2, nrows = P.lcsr_ncols;
+        const int padded = (nrows + ngrp - 1) / ngrp * ngrp;          // every warp runs every shuffle
+        int4 ri = grp < nrows ? info[grp] : make_int4(0, 0, 0, 0);
+        for (int r = grp; r < padded; r += ngrp) {
+            const int rn = r + ngrp;
+            const int4 rin = rn < nrows ? info[rn] : make_int4(0, 0, 0, 0);   // next row's descriptor in flight
+            double acc = 0.0;
+            for (int q0 = ri.y + sub; q0 < ri.z; q0 += 32) {      // eight entries per lane per round, loads batched
+                double l[8];
+                int cidx[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int q = q0 + 4 * u;
+                    const bool ok = q < ri.z;
+                    l[u] = ok ? Lcsr[q] : 0.0;
+                    cidx[u] = ok ? lcol[q] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc += l[u] * xs[cidx[u]];
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (sub == 0 && r < nrows) xs[ri.x] -= acc;
+            ri = rin;
+        }
     }
     __syncthreads();
     ps.stop(PROF_SF_BULK);
@@ -1064,18 +1090,10 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             if (bi >= 0) {
                 const int h1 = P.big[bi].h1;
                 const int *__restrict__ R = P.rows + P.rows_ptr[s];
-                if (tid < w) {   // pull from small (non-leaf, non-shared-memory) descendants
-                    double acc = 0.0;
-                    for (int q = P.fwd_ptr[c0 + tid]; q < P.fwd_ptr[c0 + tid + 1]; q++) {
-                        const FwdEntry fe = P.fwd[q];
-                        const double *Ld = pan + fe.off;
-                        for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
-                    }
-                    yv[tid] = xs[c0 + tid] - acc;
-                }
-                __syncthreads();
+                // (contributions of the small descendants were pulled in bulk after their phases)
+                const int rI = (tid >> 2) < nR ? R[tid >> 2] : 0;      // row index of this thread's push row, in flight early
                 double y0 = 0.0, y1 = 0.0;      // warp 0: unknowns lane, lane + 32 (w <= 64)
-                if (wid == 0) { y0 = lane < w ? yv[lane] : 0.0; y1 = lane + 32 < w ? yv[lane + 32] : 0.0; }
+                if (wid == 0) { y0 = lane < w ? xs[c0 + lane] : 0.0; y1 = lane + 32 < w ? xs[c0 + lane + 32] : 0.0; }
                 for (int k0 = 0; k0 < w; k0 = (k0 == 0 ? h1 : w)) {
                     const int k1 = k0 == 0 ? h1 : w;
                     issue();                                  // the slot of the previous part is free (barrier above / below)
@@ -1116,7 +1134,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                             }
                             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                            if (part == 0 && i < nR) xs[R[i]] -= acc;
+                            if (part == 0 && i < nR) xs[base == 0 ? rI : R[i]] -= acc;
                         }
                     }
                     __syncthreads();
@@ -1140,7 +1158,23 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             }
             ctx.sync();
         },
-        [&](const Ctx &, int, int, int, int) {});
+        [&](const Ctx &, int, int, int, int) {},
+        [&](int pi, int mode) {      // bulk pull: the finished phase's small supernodes -> pivot columns of chain supernodes
+            const int r0 = P.pphase_ptr[pi], r1 = P.pphase_ptr[pi + 1];
+            if (mode == 2 || r1 == r0) return;
+            const int4 *__restrict__ rowi = reinterpret_cast<const int4 *>(P.prow);
+            for (int r = r0 + tid; r < r1; r += nthr) {
+                const int4 ri = rowi[r];
+                double acc = 0.0;
+                for (int q = ri.y; q < ri.z; q++) {
+                    const FwdEntry fe = P.pfwd[q];
+                    const double *Ld = pan + fe.off;
+                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
+                }
+                xs[ri.x] -= acc;
+            }
+            __syncthreads();
+        });
     for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
@@ -1160,6 +1194,8 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                 const int h1 = P.big[bi].h1;
                 double z0 = 0.0, z1 = 0.0;      // warp 0: unknowns lane, lane + 32
                 if (wid == 0) { z0 = lane < w ? xs[c0 + lane] : 0.0; z1 = lane + 32 < w ? xs[c0 + lane + 32] : 0.0; }
+                for (int i = tid; i < nR; i += nthr) xr[i] = xs[R[i]];      // x[R] (final), staged once for both parts
+                __syncthreads();
                 for (int k1 = w; k1 > 0; k1 = (k1 == w && h1 < w ? h1 : 0)) {     // column parts in reverse order
                     const int k0 = (k1 == w && h1 < w) ? h1 : 0;
                     issue();
@@ -1173,7 +1209,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                             if (k < k1) {
                                 const double *Lc = L + k * nrow;
 #pragma unroll 4
-                                for (int r = k1 + part; r < nrow; r += 4) acc += Lc[r] * (r < w ? xs[c0 + r] : xs[R[r - w]]);
+                                for (int r = k1 + part; r < nrow; r += 4) acc += Lc[r] * (r < w ? xs[c0 + r] : xr[r - w]);
                             }
                             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -1231,17 +1267,34 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             ps.stop(PROF_SB_OTHER);
             const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.leaf_info) + begin;
             const int *__restrict__ rows = P.rows;
-            grouped_rows<4>(
-                c, end - begin,
-                [&](int q, int sub, int st) {
-                    const int4 li = info[q];        // pivot column, |R|, panel offset, rows offset
-                    const double *__restrict__ col = pan + li.z;
-                    const int *__restrict__ R = rows + li.w;
-                    double acc = 0.0;
-                    for (int i = sub; i < li.y; i += st) acc += col[i] * xs[R[i]];
-                    return acc;
-                },
-                [&](int q, double acc) { xs[info[q].x] -= acc; });
+            const int sub = tid & 3, grp = tid >> 2, ngrp = nthr >> 2, cnt = end - begin;
+            const int padded = (cnt + ngrp - 1) / ngrp * ngrp;
+            int4 li = grp < cnt ? info[grp] : make_int4(0, 0, 0, 0);    // pivot column, |R|, panel offset, rows offset
+            for (int q = grp; q < padded; q += ngrp) {
+                const int qn = q + ngrp;
+                const int4 lin = qn < cnt ? info[qn] : make_int4(0, 0, 0, 0);
+                const double *__restrict__ col = pan + li.z;
+                const int *__restrict__ R = rows + li.w;
+                double acc = 0.0;
+                for (int i0 = sub; i0 < li.y; i0 += 32) {
+                    double l[8];
+                    int ridx[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = i0 + 4 * u;
+                        const bool ok = i < li.y;
+                        l[u] = ok ? col[i] : 0.0;
+                        ridx[u] = ok ? R[i] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc += l[u] * xs[ridx[u]];
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (sub == 0 && q < cnt) xs[li.x] -= acc;
+                li = lin;
+            }
+            (void)c;
             __syncthreads();
             ps.stop(PROF_SB_LEAVES);
         });

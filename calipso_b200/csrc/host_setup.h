@@ -172,6 +172,7 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.kx_total = S.kx_total;
     P.big_seq = up(S.big_seq); P.big_seq_bwd = up(S.big_seq_bwd); P.nbig = (int)S.big_seq.size(); P.max_sb_doubles = S.max_sb_doubles;
     P.solve_smem = S.solve_smem;
+    P.pfwd = up(S.pfwd); P.prow = up(S.prow); P.pphase_ptr = up(S.pphase_ptr); P.max_big_nR = S.max_big_nR;
     P.parts_fwd = up(S.parts_fwd); P.parts_bwd = up(S.parts_bwd);
     P.nparts_fwd = (int)S.parts_fwd.size() / 2; P.nparts_bwd = (int)S.parts_bwd.size() / 2;
     P.lcsr_ptr = up(S.lcsr_ptr); P.lcsr_col = up(S.lcsr_col); P.leaf_csr_pos = up(S.leaf_csr_pos);

@@ -450,7 +450,10 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                 if (big_index[order[q]] >= 0) big_seq_bwd.push_back(order[q]);
     {   // shared-memory solve: the permuted vector, two part buffers (TMA double buffering), one pivot window
         max_sb_doubles = (max_sb_doubles + 1) & ~1;
-        long long need = (((long long)N + 1) & ~1LL) + 2LL * max_sb_doubles + 64 + 16;
+        int max_nR_big = 0;
+        for (int t = 0; t < ns; t++)
+            if (big_index[t] >= 0) max_nR_big = std::max(max_nR_big, rows_ptr[t + 1] - rows_ptr[t]);
+        long long need = (((long long)N + 1) & ~1LL) + 2LL * max_sb_doubles + 64 + 16 + ((max_nR_big + 1) & ~1);
         solve_smem = (!big.empty() && need <= smem_budget_doubles) ? 1 : 0;
         if (solve_smem) scratch_doubles = (int)std::max<long long>(scratch_doubles, need);
         parts_fwd.clear(); parts_bwd.clear();
@@ -499,6 +502,39 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                 }
             }
         }
+    }
+    {   // per-phase bulk pulls into the pivot columns of the shared-memory supernodes
+        std::vector<int> phase_of(ns, 0);
+        for (size_t pi = 0; pi < phases.size(); pi++)
+            for (int q = phases[pi].begin; q < phases[pi].end; q++) phase_of[order[q]] = (int)pi;
+        struct Item { int phase, col; FwdEntry fe; };
+        std::vector<Item> items;
+        for (int d = 0; d < ns; d++) {
+            if (is_single_leaf(d) || big_index[d] >= 0) continue;
+            const int wd = sn_start[d + 1] - sn_start[d], nrowd = wd + rows_ptr[d + 1] - rows_ptr[d];
+            for (int q = rows_ptr[d]; q < rows_ptr[d + 1]; q++) {
+                const int c = rows[q];
+                if (big_index[sn_of[c]] < 0) continue;
+                items.push_back(Item{phase_of[d], c, FwdEntry{(int)panel_off[d] + wd + (q - rows_ptr[d]), sn_start[d], wd, nrowd}});
+            }
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+            return a.phase != b.phase ? a.phase < b.phase : a.col < b.col;
+        });
+        pfwd.clear(); prow.clear();
+        pphase_ptr.assign(phases.size() + 1, 0);
+        for (size_t i = 0; i < items.size();) {
+            size_t j = i;
+            while (j < items.size() && items[j].phase == items[i].phase && items[j].col == items[i].col) j++;
+            prow.insert(prow.end(), {items[i].col, (int)pfwd.size(), (int)(pfwd.size() + (j - i)), 0});
+            for (size_t k = i; k < j; k++) pfwd.push_back(items[k].fe);
+            pphase_ptr[items[i].phase + 1]++;
+            i = j;
+        }
+        for (size_t pi = 0; pi < phases.size(); pi++) pphase_ptr[pi + 1] += pphase_ptr[pi];
+        max_big_nR = 0;
+        for (int t = 0; t < ns; t++)
+            if (big_index[t] >= 0) max_big_nR = std::max(max_big_nR, rows_ptr[t + 1] - rows_ptr[t]);
     }
     lcsr_cols.clear();
     lcsr_rowinfo.clear();

@@ -81,6 +81,12 @@ struct Symbolic {
     // and are pulled in one bulk pass from a row-ordered (CSR) copy of the leaf columns written by the factorisation.
     std::vector<int> fwd_ptr;
     std::vector<FwdEntry> fwd;       // non-leaf descendants only
+    // the same contributions for the pivot columns of the shared-memory supernodes only, grouped by the PHASE of the
+    // contributing descendant: pulled in bulk right after that phase, so that the chain steps do no pulling at all
+    std::vector<FwdEntry> pfwd;
+    std::vector<int> prow;           // 4 ints per (phase, column): column, begin and end in pfwd, 0
+    std::vector<int> pphase_ptr;     // [phases + 1] range of prow rows per phase
+    int max_big_nR = 0;              // largest |R| of a shared-memory supernode (row window of the backward solve)
     std::vector<int> lcsr_ptr;       // [N+1] per permuted column: range in lcsr_col / the Lcsr value array
     std::vector<int> lcsr_col;       // pivot column of the leaf
     std::vector<int> leaf_csr_pos;   // [rows.size()] for entry q of rows[] of a singleton leaf: its position in Lcsr (-1 else)

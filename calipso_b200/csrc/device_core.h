@@ -73,6 +73,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     int n_gasm, n_gasm_zero;
     long long lcsr_total;
     const int *leaf_e_off, *leaf_e_col, *leaf_e_pos;   // flat below-diagonal entries of the singleton leaves
+    const int *leaf_e4;                                // the same, packed: {panel offset, pivot column, Lcsr position, value code}
     const int *big_index;                      // [ns] -> big[] (shared-memory path) or -1
     const BigTarget *big;
     const YChunk *ychunks;
@@ -949,28 +950,30 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
             }
             ctx.sync();
             {                               // entries, leaf by leaf => coalesced panel accesses
-                const int *__restrict__ eo = P.leaf_e_off + ebegin, *__restrict__ ec = P.leaf_e_col + ebegin,
-                                        *__restrict__ ep = P.leaf_e_pos + ebegin, *__restrict__ es = P.leaf_e_src + ebegin;
                 const int cnt = eend - ebegin;
 #if CB_ON_DEVICE
+                const int4 *__restrict__ e4 = reinterpret_cast<const int4 *>(P.leaf_e4) + ebegin;
                 int e = ctx.tid;
                 const int st = ctx.nthr;
                 for (; e + 3 * st < cnt; e += 4 * st) {
-                    int o[4], pp[4], sc[4], cc[4];
+                    int4 d[4];
                     double v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { o[u] = eo[e + u * st]; pp[u] = ep[e + u * st]; sc[u] = es[e + u * st]; cc[u] = ec[e + u * st]; }
+                    for (int u = 0; u < 4; u++) d[u] = e4[e + u * st];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = ksrc_load(K, sc[u]) * Dinv[cc[u]];
+                    for (int u = 0; u < 4; u++) v[u] = ksrc_load(K, d[u].w) * Dinv[d[u].y];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { pan[o[u]] = v[u]; Lcsr[pp[u]] = v[u]; }
+                    for (int u = 0; u < 4; u++) { pan[d[u].x] = v[u]; Lcsr[d[u].z] = v[u]; }
                 }
                 for (; e < cnt; e += st) {
-                    const double l = ksrc_load(K, es[e]) * Dinv[ec[e]];
-                    pan[eo[e]] = l;
-                    Lcsr[ep[e]] = l;
+                    const int4 d = e4[e];
+                    const double l = ksrc_load(K, d.w) * Dinv[d.y];
+                    pan[d.x] = l;
+                    Lcsr[d.z] = l;
                 }
 #else
+                const int *eo = P.leaf_e_off + ebegin, *ec = P.leaf_e_col + ebegin, *ep = P.leaf_e_pos + ebegin,
+                          *es = P.leaf_e_src + ebegin;
                 for (int e = 0; e < cnt; e++) {
                     const double l = ksrc_load(K, es[e]) * Dinv[ec[e]];
                     pan[eo[e]] = l;

@@ -130,6 +130,7 @@ struct HostProblem {
             for (int i = 0; i < q_nn; i++) code[eZnn[i]] = (int)((3u << 30) | (unsigned)(n + m + i));
             for (int t = 0; t < tri; t++) code[eZsoc[t]] = (int)((3u << 30) | (unsigned)(n + m + q_nn + t));
             sym.map_sources([&](int e) { return code[e]; });
+            sym.pack_leaf_entries();
             sym.kx_total = (long long)n + m + q_nn + tri;
         }
         return "";
@@ -179,7 +180,7 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.lcsr_total = S.lcsr_total;
     P.lcsr_cols = up(S.lcsr_cols); P.lcsr_ncols = (int)S.lcsr_cols.size();
     P.lcsr_rowinfo = up(S.lcsr_rowinfo); P.leaf_info = up(S.leaf_info);
-    P.leaf_e_src = up(S.leaf_e_src); P.leaf_piv_src = up(S.leaf_piv_src);
+    P.leaf_e_src = up(S.leaf_e_src); P.leaf_piv_src = up(S.leaf_piv_src); P.leaf_e4 = up(S.leaf_e4);
     P.basm_src = up(S.basm_src); P.basm_dst = up(S.basm_dst);
     P.gasm_src = up(S.gasm_src); P.gasm_dst = up(S.gasm_dst); P.gasm_zero = up(S.gasm_zero);
     P.n_gasm = (int)S.gasm_src.size(); P.n_gasm_zero = (int)S.gasm_zero.size();

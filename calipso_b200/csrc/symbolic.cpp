@@ -627,6 +627,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             if (bi >= 0) big[bi].asm_end = (int)basm_src.size();
         }
     }
+    pack_leaf_entries();
     return "";
 }
 

@@ -98,6 +98,15 @@ struct Symbolic {
     // flat list of the below-diagonal entries of the singleton leaves, grouped by phase, leaf by leaf: panel offset of
     // the entry, pivot column of its leaf, position of its row-ordered copy in Lcsr
     std::vector<int> leaf_e_off, leaf_e_col, leaf_e_pos;
+    std::vector<int> leaf_e4;        // packed {offset, column, position, value code} (filled by pack_leaf_entries)
+    void pack_leaf_entries()
+    {
+        leaf_e4.resize(4 * leaf_e_off.size());
+        for (size_t e = 0; e < leaf_e_off.size(); e++) {
+            leaf_e4[4 * e] = leaf_e_off[e]; leaf_e4[4 * e + 1] = leaf_e_col[e];
+            leaf_e4[4 * e + 2] = leaf_e_pos[e]; leaf_e4[4 * e + 3] = leaf_e_src[e];
+        }
+    }
     // shared-memory path for big targets
     std::vector<int> big_index;   // [ns] index into big, or -1
     std::vector<BigTarget> big;

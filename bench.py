@@ -221,13 +221,20 @@ def run_gpu(args):
             ms = float(t.item())
         return ms
 
-    launches = [0]
+    launches = [0, 0]              # all kernels of this library, k_lq_step launches
+    lq_ms = [0.0]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
     def one_solve():
         k.initialize(X0)           # H2D of the primal guesses is part of a solve! call (initialize!, initialize.jl:9)
         k.lq_begin()
-        r = k.lq_solve(max_steps=args.max_newton, check_every=args.check_every)
+        ev[0].record(stream)
+        r = k.lq_solve(max_steps=args.max_newton, check_every=args.check_every)   # syncs at every convergence check
+        ev[1].record(stream)
+        ev[1].synchronize()
+        lq_ms[0] += ev[0].elapsed_time(ev[1])
         launches[0] += 1 + r["steps"] + (r["steps"] + args.check_every - 1) // args.check_every
+        launches[1] += r["steps"]
         return r
 
     for _ in range(args.warmup):
@@ -243,7 +250,9 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches[0] = 0
+    launches[:] = [0, 0]
+    lq_ms[0] = 0.0
+    st0 = {kk: v.copy() for kk, v in k.stats().items()}
     ms_step = timed(one_solve, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = total_iters / (ms_step * 1e-3)
@@ -251,6 +260,23 @@ def run_gpu(args):
     conv = k.allreduce_counts()
     stats = {kk: v for kk, v in k.stats().items()}
 
+    # ---- dominant kernel of the step: k_lq_step (one Newton iteration of every running instance per launch).
+    # Algorithmic bytes = SURVEY.md section 8(d): per instance B_newton = B_res + B_cone + n_trials (B_asm + B_factor)
+    # + (1 + n_refine) (B_solve + B_spmv), with the factorisation / solve counts the kernel actually performed.
+    P0 = Ps[0]
+    nW, nG, nC = len(P0.W_rowval), len(P0.G_rowval), len(P0.C_rowval)
+    N_, T_, nK, nL = info["N"], info["total"], info["nnzK"], info["nnzL"]
+    b_asm = 12 * (nW + nG + nC) + 8 * nK
+    b_factor = 12 * nK + 12 * nL + 16 * N_
+    b_solve = 24 * nL + 24 * N_
+    b_spmv = 12 * ((2 * nW - info["n"]) + 2 * nG + 2 * nC) + 16 * T_
+    b_res = 8 * (2 * T_ + 3 * info["n"] + 2 * info["m"] + info["p"])
+    b_cone = 80 * info["p"]
+    d_fact = int((stats["factorizations"] - st0["factorizations"]).sum())
+    d_solv = int((stats["solves"] - st0["solves"]).sum())
+    newton_bytes = d_fact * (b_asm + b_factor) + d_solv * (b_solve + b_spmv) + args.steps * iters_per_solve * (b_res + b_cone)
+    n_lq_launches = launches[1]
+    ms_lq_launch = lq_ms[0] / max(n_lq_launches, 1)
     # ---- dominant kernel: KKT factor + solve (assemble + LDL^T + one reduced solve with recovery), roofline vs HBM
     k.lq_begin()
     k.lq_step(4)                   # realistic interior point
@@ -264,15 +290,25 @@ def run_gpu(args):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = b_unit * B / (ms_kkt * 1e-3) / 1e9
-    traffic = None
+    kkt_achieved = b_unit * B / (ms_kkt * 1e-3) / 1e9
+    tpath2 = os.path.join(ROOT, "profiles", "lq_step_traffic.json")
+    traffic = json.load(open(tpath2)).get("dram_bytes_per_launch") if os.path.exists(tpath2) else None
     tpath = os.path.join(ROOT, "profiles", "kkt_factor_solve_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    kkt_traffic = json.load(open(tpath)).get("dram_bytes_per_launch") if os.path.exists(tpath) else None
+    achieved = newton_bytes / max(n_lq_launches, 1) / (ms_lq_launch * 1e-3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    kernel="k_kkt_factor_solve", algorithmic_bytes_per_kkt_solve=b_unit, kkt_solves_per_launch=B,
-                    ms_per_launch=ms_kkt, kkt_solve_ms_per_instance_batched=ms_kkt / B, peak_source=peak_src)
-
+                    kernel="k_lq_step", launches_in_timed_region=n_lq_launches, ms_per_launch=ms_lq_launch,
+                    algorithmic_bytes_per_launch=newton_bytes / max(n_lq_launches, 1),
+                    algorithmic_bytes_formula="SURVEY 8(d): n_fact*(B_asm+B_factor) + n_solves*(B_solve+B_spmv) + n_newton*(B_res+B_cone)",
+                    factorizations=d_fact, reduced_solves=d_solv, peak_source=peak_src,
+                    note="launch duration = CUDA events around cb200_lq_solve on the handle's stream / k_lq_step launches "
+                         "(includes the per-check 32-byte counter read-back); converged instances are masked, so late "
+                         "launches carry fewer bytes",
+                    kkt_solve=dict(kernel="k_kkt_factor_solve", achieved=kkt_achieved, frac=kkt_achieved / peak,
+                                   algorithmic_bytes_per_kkt_solve=b_unit, kkt_solves_per_launch=B, ms_per_launch=ms_kkt,
+                                   kkt_solve_ms_per_instance_batched=ms_kkt / B, traffic=kkt_traffic,
+                                   what="assemble + LDL' factor + 1 reduced solve with recovery per instance: the 'KKT solve' "
+                                        "unit of SURVEY 8(d), B_unit = 12 nnz(K) + 36 nnz(L) + 40 N"))
     # ---- e2e: the reference-facing hot path through the C ABI with HOST buffers (pinned), copies inside the timing
     k.lq_begin()
     k.lq_step(4)

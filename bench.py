@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=444, help="instances per GPU (3 resident CTAs per SM x 148 SMs)")
+    ap.add_argument("--batch", type=int, default=1332, help="instances per GPU (9 per SM: three waves of 3 resident CTAs x 148 SMs)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct seeds per GPU, tiled over the batch")
     ap.add_argument("--max-newton", type=int, default=400)
     ap.add_argument("--check-every", type=int, default=4)

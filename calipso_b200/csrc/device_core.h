@@ -1491,6 +1491,31 @@ CB_DEVN void recover_step(const Ctx &ctx, const DevProblem &P, const Inst &I, co
 }
 
 // ------------------------------------------------------------------------------------------------ J * v (matrix-free)
+#if CB_ON_DEVICE
+// lane `sub` of a 4-lane group: sum over k = k0 + sub, k0 + sub + 4, ... < k1 of vals[src[k]] * vec[col[k]] (src == nullptr:
+// vals[k]); eight entries per round with the index loads, then the value loads, batched
+__device__ __forceinline__ double sparse_dot4(const double *__restrict__ vals, const int *__restrict__ src,
+                                              const int *__restrict__ col, const double *vec, int k0, int k1, int sub)
+{
+    double acc = 0.0;
+    for (int q0 = k0 + sub; q0 < k1; q0 += 32) {
+        int si[8], ci[8];
+        double vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int q = q0 + 4 * u;
+            const bool ok = q < k1;
+            ci[u] = ok ? col[q] : 0;
+            si[u] = ok ? (src ? src[q] : q) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) vv[u] = si[u] >= 0 ? vals[si[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += vv[u] * vec[ci[u]];
+    }
+    return acc;
+}
+#endif
 CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *v, double *out)
 {
     const int n = P.n, m = P.m, p = P.p;
@@ -1502,28 +1527,80 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
         const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col, *__restrict__ ws = P.Wfull.src;
         const int *__restrict__ gp = P.Gp, *__restrict__ gi = P.Gi, *__restrict__ cp = P.Cp, *__restrict__ ci = P.Ci;
         const double *__restrict__ Wv = I.Wv, *__restrict__ Gv = I.Gv, *__restrict__ Cv = I.Cv;
-        grouped_rows<4>(
-            ctx, n,
-            [&](int i, int sub, int st) {
-                double a = 0.0;
-                for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += Wv[ws[k]] * vx[wc[k]];
-                for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += Gv[k] * vy[gi[k]];
-                for (int k = cp[i] + sub; k < cp[i + 1]; k += st) a += Cv[k] * vz[ci[k]];
-                return a;
-            },
-            [&](int i, double a) { out[i] = ep * vx[i] + a; });
         const int *__restrict__ grp = P.Grow.ptr, *__restrict__ grc = P.Grow.col, *__restrict__ grs = P.Grow.src;
-        grouped_rows<4>(
-            ctx, m,
-            [&](int i, int sub, int st) {
-                double a = 0.0;
-                for (int k = grp[i] + sub; k < grp[i + 1]; k += st) a += Gv[grs[k]] * vx[grc[k]];
-                return a;
-            },
-            [&](int i, double a) {
-                out[n + i] = (rho + ep) * vr[i] - vy[i];
-                out[n + m + p + i] = a - vr[i] - ed * vy[i];
-            });
+#if CB_ON_DEVICE
+        unsigned dyn_bytes;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        if (!ctx.warp_scope && dyn_bytes >= (unsigned)P.N * 8u) {
+            // the gathered parts of v (x, y, z blocks) are staged in shared memory; four lanes per sparse row with the
+            // row pointers of the next row in flight
+            double *sx = cb_dyn_smem, *sy = sx + n, *sz = sy + m;
+            for (int k = ctx.tid; k < n; k += ctx.nthr) sx[k] = vx[k];
+            for (int k = ctx.tid; k < m; k += ctx.nthr) sy[k] = vy[k];
+            for (int k = ctx.tid; k < p; k += ctx.nthr) sz[k] = vz[k];
+            __syncthreads();
+            const int sub = threadIdx.x & 3, gidx = threadIdx.x >> 2, ngrp = blockDim.x >> 2;
+            {
+                const int padded = (n + ngrp - 1) / ngrp * ngrp;
+                int i = gidx;
+                int w0 = i < n ? wp[i] : 0, w1 = i < n ? wp[i + 1] : 0, g0 = i < n ? gp[i] : 0, g1 = i < n ? gp[i + 1] : 0,
+                    c0 = i < n ? cp[i] : 0, c1 = i < n ? cp[i + 1] : 0;
+                for (; i < padded; i += ngrp) {
+                    const int in = i + ngrp;
+                    const bool okn = in < n;
+                    const int nw0 = okn ? wp[in] : 0, nw1 = okn ? wp[in + 1] : 0, ng0 = okn ? gp[in] : 0,
+                              ng1 = okn ? gp[in + 1] : 0, nc0 = okn ? cp[in] : 0, nc1 = okn ? cp[in + 1] : 0;
+                    double a = sparse_dot4(Wv, ws, wc, sx, w0, w1, sub) + sparse_dot4(Gv, nullptr, gi, sy, g0, g1, sub);
+                    for (int k = c0 + sub; k < c1; k += 4) a += Cv[k] * sz[ci[k]];
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    if (sub == 0 && i < n) out[i] = ep * sx[i] + a;
+                    w0 = nw0; w1 = nw1; g0 = ng0; g1 = ng1; c0 = nc0; c1 = nc1;
+                }
+            }
+            {
+                const int padded = (m + ngrp - 1) / ngrp * ngrp;
+                int i = gidx;
+                int a0 = i < m ? P.Grow.ptr[i] : 0, a1 = i < m ? P.Grow.ptr[i + 1] : 0;
+                for (; i < padded; i += ngrp) {
+                    const int in = i + ngrp;
+                    const int na0 = in < m ? P.Grow.ptr[in] : 0, na1 = in < m ? P.Grow.ptr[in + 1] : 0;
+                    double a = sparse_dot4(Gv, grs, grc, sx, a0, a1, sub);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    if (sub == 0 && i < m) {
+                        out[n + i] = (rho + ep) * vr[i] - sy[i];
+                        out[n + m + p + i] = a - vr[i] - ed * sy[i];
+                    }
+                    a0 = na0; a1 = na1;
+                }
+            }
+            __syncthreads();
+        } else
+#endif
+        {
+            grouped_rows<4>(
+                ctx, n,
+                [&](int i, int sub, int st) {
+                    double a = 0.0;
+                    for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += Wv[ws[k]] * vx[wc[k]];
+                    for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += Gv[k] * vy[gi[k]];
+                    for (int k = cp[i] + sub; k < cp[i + 1]; k += st) a += Cv[k] * vz[ci[k]];
+                    return a;
+                },
+                [&](int i, double a) { out[i] = ep * vx[i] + a; });
+            grouped_rows<4>(
+                ctx, m,
+                [&](int i, int sub, int st) {
+                    double a = 0.0;
+                    for (int k = grp[i] + sub; k < grp[i + 1]; k += st) a += Gv[grs[k]] * vx[grc[k]];
+                    return a;
+                },
+                [&](int i, double a) {
+                    out[n + i] = (rho + ep) * vr[i] - vy[i];
+                    out[n + m + p + i] = a - vr[i] - ed * vy[i];
+                });
+        }
     }
     PAR_FOR(i, p) {
         out[n + m + i] = ep * vs[i] - vz[i] - vt[i];

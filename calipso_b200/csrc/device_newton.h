@@ -18,40 +18,65 @@ CB_DEVN void lq_evaluate(const Ctx &ctx, const DevProblem &P, const Inst &I, con
 {
     const int n = P.n, m = P.m, p = P.p;
     const double *x = w, *y = w + n + m + p, *z = w + n + 2 * m + p;
+    // sparse rows by groups of four lanes (grouped_rows): short dependent-load chains, coalesced index reads
     if (flags & (EV_OBJECTIVE | EV_GRADIENT)) {
-        double f = scope_sum(ctx, n, [&](int i) {
-            double a = 0.0;
-            for (int k = P.Wfull.ptr[i]; k < P.Wfull.ptr[i + 1]; k++) a += I.Wv[P.Wfull.src[k]] * x[P.Wfull.col[k]];
-            if (flags & EV_GRADIENT) I.grad[i] = a + I.q[i];
-            return x[i] * (0.5 * a + I.q[i]);
-        });
-        if ((flags & EV_OBJECTIVE) && ctx.tid == 0) I.scal[S_OBJECTIVE] = f;
-    }
-    if (flags & EV_EQUALITY)
-        PAR_FOR(i, m) {
-            double a = I.g0[i];
-            for (int k = P.Grow.ptr[i]; k < P.Grow.ptr[i + 1]; k++) a += I.Gv[P.Grow.src[k]] * x[P.Grow.col[k]];
-            I.g[i] = a;
+        const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col, *__restrict__ ws = P.Wfull.src;
+        const double *__restrict__ Wv = I.Wv;
+        double *red = I.tmp;       // per-row terms of the objective (summed below in a fixed order)
+        grouped_rows<4>(
+            ctx, n,
+            [&](int i, int sub, int st) {
+                double a = 0.0;
+                for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += Wv[ws[k]] * x[wc[k]];
+                return a;
+            },
+            [&](int i, double a) {
+                if (flags & EV_GRADIENT) I.grad[i] = a + I.q[i];
+                red[i] = x[i] * (0.5 * a + I.q[i]);
+            });
+        ctx.sync();
+        if (flags & EV_OBJECTIVE) {
+            double f = scope_sum(ctx, n, [&](int i) { return red[i]; });
+            if (ctx.tid == 0) I.scal[S_OBJECTIVE] = f;
         }
+    }
+    if (flags & EV_EQUALITY) {
+        const int *__restrict__ gp = P.Grow.ptr, *__restrict__ gc = P.Grow.col, *__restrict__ gs = P.Grow.src;
+        const double *__restrict__ Gv = I.Gv;
+        grouped_rows<4>(
+            ctx, m,
+            [&](int i, int sub, int st) {
+                double a = 0.0;
+                for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += Gv[gs[k]] * x[gc[k]];
+                return a;
+            },
+            [&](int i, double a) { I.g[i] = I.g0[i] + a; });
+    }
     if (flags & EV_CONE)
         PAR_FOR(i, p) {
             double a = I.h0[i];
             for (int k = P.Crow.ptr[i]; k < P.Crow.ptr[i + 1]; k++) a += I.Cv[P.Crow.src[k]] * x[P.Crow.col[k]];
             I.h[i] = a;
         }
-    if (flags & (EV_EQUALITY_DUAL_GRAD | EV_CONE_DUAL_GRAD))
-        PAR_FOR(j, n) {
-            if (flags & EV_EQUALITY_DUAL_GRAD) {
+    if (flags & (EV_EQUALITY_DUAL_GRAD | EV_CONE_DUAL_GRAD)) {
+        const int *__restrict__ gp = P.Gp, *__restrict__ gi = P.Gi, *__restrict__ cp = P.Cp, *__restrict__ ci = P.Ci;
+        const double *__restrict__ Gv = I.Gv, *__restrict__ Cv = I.Cv;
+        if (flags & EV_EQUALITY_DUAL_GRAD)
+            grouped_rows<4>(
+                ctx, n,
+                [&](int j, int sub, int st) {
+                    double a = 0.0;
+                    for (int k = gp[j] + sub; k < gp[j + 1]; k += st) a += Gv[k] * y[gi[k]];
+                    return a;
+                },
+                [&](int j, double a) { I.gyx[j] = a; });
+        if (flags & EV_CONE_DUAL_GRAD)
+            PAR_FOR(j, n) {
                 double a = 0.0;
-                for (int k = P.Gp[j]; k < P.Gp[j + 1]; k++) a += I.Gv[k] * y[P.Gi[k]];
-                I.gyx[j] = a;
-            }
-            if (flags & EV_CONE_DUAL_GRAD) {
-                double a = 0.0;
-                for (int k = P.Cp[j]; k < P.Cp[j + 1]; k++) a += I.Cv[k] * z[P.Ci[k]];
+                for (int k = cp[j]; k < cp[j + 1]; k++) a += Cv[k] * z[ci[k]];
                 I.hzx[j] = a;
             }
-        }
+    }
     ctx.sync();
 }
 

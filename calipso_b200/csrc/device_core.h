@@ -1070,10 +1070,11 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                     const int q = q0 + 4 * u;
                     const bool ok = q < ri.z;
                     l[u] = ok ? Lcsr[q] : 0.0;
-                    cidx[u] = ok ? lcol[q] : 0;
+                    cidx[u] = ok ? lcol[q] : -1;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) acc += l[u] * xs[cidx[u]];
+                for (int u = 0; u < 8; u++)
+                    if (cidx[u] >= 0) acc += l[u] * xs[cidx[u]];
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -1287,10 +1288,11 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                         const int i = i0 + 4 * u;
                         const bool ok = i < li.y;
                         l[u] = ok ? col[i] : 0.0;
-                        ridx[u] = ok ? R[i] : 0;
+                        ridx[u] = ok ? R[i] : -1;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; u++) acc += l[u] * xs[ridx[u]];
+                    for (int u = 0; u < 8; u++)
+                        if (ridx[u] >= 0) acc += l[u] * xs[ridx[u]];      // (no stray reads of entries other groups write)
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);

@@ -95,6 +95,7 @@ SYMBOLS = {
     "cb200_apply_step": (C.c_int, [vp]),
     "cb200_kkt_factor_solve": (C.c_int, [vp, C.c_int]),
     "cb200_jacobian_times": (C.c_int, [vp, c_dp, c_dp]),
+    "cb200_differentiate": (C.c_int, [vp, C.c_int, c_dp, c_dp]),
     "cb200_lq_evaluate": (C.c_int, [vp, C.c_int, C.c_int]),
     "cb200_lq_begin": (C.c_int, [vp, C.c_int]),
     "cb200_lq_step": (C.c_int, [vp, C.c_int]),

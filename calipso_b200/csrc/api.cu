@@ -194,6 +194,23 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(co
     PROF_FLUSH(I.prof);
 }
 
+// differentiate!: one factorisation, num_parameters reduced solves with recovery, sign flip (differentiate.jl:13-57)
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_differentiate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nparam,
+                                                                         const double *H, double *S)
+{
+    KERNEL_PROLOGUE
+    kkt_entries(ctx, P, I);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
+    for (int i = 0; i < nparam; i++) {
+        const double *rhs = H + ((long long)b * nparam + i) * P.total;
+        double *out = S + ((long long)b * nparam + i) * P.total;
+        direction_symmetric(ctx, P, I, rhs, out);
+        PAR_FOR(k, P.total) out[k] = -1.0 * out[k];
+        ctx.sync();
+    }
+    PROF_FLUSH(I.prof);
+}
+
 __global__ void k_count_states(Batch B, long long *counts)
 {
     __shared__ int c[4];
@@ -578,6 +595,34 @@ extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
     return 0;
 }
 extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); LAUNCH_SMEM(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
+
+extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_host, double *S_host)
+{
+    NEED_KKT();
+    if (nparam <= 0) return 0;
+    CUDA_OK(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * (size_t)h->batch * (size_t)nparam * (size_t)h->P.total;
+    double *dH = nullptr, *dS = nullptr;
+    CUDA_OK(cudaMalloc(&dH, bytes));
+    if (cudaMalloc(&dS, bytes) != cudaSuccess) { cudaFree(dH); return fail("cb200_differentiate: device allocation failed"); }
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(dH, H_host, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = fail("H2D failed"); break; }
+        static size_t configured = 0;
+        if (h->smem_bytes > configured) {
+            if (cudaFuncSetAttribute(k_differentiate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            configured = h->smem_bytes;
+        }
+        k_differentiate<<<h->batch, CB_THREADS, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS);
+        if (cudaGetLastError() != cudaSuccess) { rc = fail("k_differentiate launch failed"); break; }
+        if (cudaMemcpyAsync(S_host, dS, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = fail("D2H failed"); break; }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { rc = fail(std::string("cb200_differentiate: ") + cudaGetErrorString(e)); break; }
+    } while (0);
+    cudaFree(dH);
+    cudaFree(dS);
+    return rc;
+}
 
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host)
 {

@@ -210,6 +210,21 @@ class BatchKKT:
     def kkt_factor_solve(self, nsolves=1):
         self.b.check(self.lib.cb200_kkt_factor_solve(self.h, nsolves))
 
+    def differentiate(self, jacobian_parameters):
+        """differentiate!(solver), src/solver/differentiate.jl:1-61: solution sensitivities dw/dtheta at the current point.
+        jacobian_parameters: [batch, total, num_parameters] (or [total, num_parameters] for batch 1) = dR/dtheta
+        (residual_jacobian_parameters!); returns solution_sensitivity in the same shape."""
+        H = f64(jacobian_parameters)
+        if H.ndim == 2:
+            H = H[None]
+        assert H.shape[0] == self.batch and H.shape[1] == self.total
+        nparam = H.shape[2]
+        Hc = np.ascontiguousarray(np.transpose(H, (0, 2, 1)))          # column i contiguous
+        out = np.zeros_like(Hc)
+        self.b.check(self.lib.cb200_differentiate(self.h, nparam, dp(Hc), dp(out)))
+        S = np.transpose(out, (0, 2, 1))
+        return S[0] if np.ndim(jacobian_parameters) == 2 else S
+
     def jacobian_times(self, v):
         v = f64(v).reshape(self.batch, self.total)
         out = np.zeros_like(v)

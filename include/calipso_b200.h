@@ -174,6 +174,14 @@ int cb200_apply_step(cb200_handle *h);
  * then `nsolves` x (residual_symmetric! + solve! + recovery) of the current residual -- the "KKT solve" unit of
  * SURVEY.md section 8(d) */
 int cb200_kkt_factor_solve(cb200_handle *h, int nsolves);
+/* differentiate!(solver), src/solver/differentiate.jl:1-61: ONE factorisation of the
+ * reduced matrix at the current point and the current (eps_p, eps_d) (:13-20), then per parameter one
+ * search_direction_symmetric! (reduced rhs + LDL' solve + recovery, no refinement, :35-46) on column i of
+ * residual_jacobian_parameters! (residual_jacobian_parameters.jl:1-40), and solution_sensitivity[:, i] = -result (:55-57).
+ * (The reference re-factors for every parameter; the factor is reused here.)  Host buffers, instance-major:
+ * jacobian_parameters[b][i][total] (column i contiguous), sensitivity[b][i][total]. */
+int cb200_differentiate(cb200_handle *h, int num_parameters, const double *jacobian_parameters_host,
+                        double *sensitivity_host);
 /* out = J v for instance-major v (mul! with jacobian_variables, iterative_refinement.jl:9) -- tests / glue */
 int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host);
 

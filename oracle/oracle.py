@@ -332,6 +332,23 @@ class Oracle:
         self.L.orc_search_direction_symmetric(self.h, _dp(st), _dp(r), int(factorize))
         return st
 
+    def differentiate(self, jacobian_parameters):
+        """differentiate!(solver), src/solver/differentiate.jl:1-61, given dR/dtheta (total x num_parameters,
+        residual_jacobian_parameters.jl:1-40): rebuild and factor the reduced matrix at the current point and
+        regularisation (:13-20), one search_direction_symmetric! per parameter (it re-factors every time, :35-46;
+        same matrix), solution_sensitivity[:, i] = -result (:55-57)."""
+        H = np.asarray(jacobian_parameters, dtype=np.float64)
+        self.residual_jacobian_variables()
+        self.residual_jacobian_variables_symmetric()
+        self.factorize()
+        S = np.zeros_like(H)
+        for i in range(H.shape[1]):
+            col = np.ascontiguousarray(H[:, i])
+            st = np.zeros(self.total)
+            self.search_direction_symmetric(step=st, residual=col, factorize=True)
+            S[:, i] = -1.0 * st
+        return S
+
     def iterative_refinement(self, step=None):
         st = self.step if step is None else step
         return bool(self.L.orc_iterative_refinement(self.h, _dp(st)))

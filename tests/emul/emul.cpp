@@ -274,6 +274,20 @@ extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves)
     END_FOR
     return 0;
 }
+extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H, double *S)
+{
+    FOR_EACH_INSTANCE
+        kkt_entries(ctx, P, I);
+        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, nullptr);
+        for (int i = 0; i < nparam; i++) {
+            const double *rhs = H + ((long long)b * nparam + i) * P.total;
+            double *out = S + ((long long)b * nparam + i) * P.total;
+            direction_symmetric(ctx, P, I, rhs, out);
+            for (int k = 0; k < P.total; k++) out[k] = -1.0 * out[k];
+        }
+    END_FOR
+    return 0;
+}
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v, double *out)
 {
     FOR_EACH_INSTANCE jacobian_times(ctx, P, I, v + (long long)b * P.total, out + (long long)b * P.total); END_FOR

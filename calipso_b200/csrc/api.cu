@@ -64,6 +64,12 @@ struct Batch {
 #define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
 #define CTX_SETUP                                                                                          \
     if (threadIdx.x < 32) cb_prof[threadIdx.x] = 0;                                                        \
+    {                                                                                                      \
+        const int nch = P.nbig <= CB_MAX_CHAIN ? P.nbig : 0;                                               \
+        if (threadIdx.x == 0) cb_chain_n = nch;                                                            \
+        for (int e = threadIdx.x; e < 2 * nch; e += blockDim.x)                                            \
+            cb_chain[e] = reinterpret_cast<const int4 *>(P.bdesc)[e];                                      \
+    }                                                                                                      \
     if (threadIdx.x == 0) {                                                                                \
         mbar_init(&cb_bars[0], 1);                                                                         \
         mbar_init(&cb_bars[1], 1);                                                                         \

@@ -76,6 +76,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const int *leaf_e4;                                // the same, packed: {panel offset, pivot column, Lcsr position, value code}
     const int *big_index;                      // [ns] -> big[] (shared-memory path) or -1
     const BigTarget *big;
+    const ChainDesc *bdesc;                    // [nbig] packed descriptors (copied to shared memory when nbig <= CB_MAX_CHAIN)
     const YChunk *ychunks;
     const int *ystage_src, *ystage_dst, *ypiv;
     const unsigned *ymask;
@@ -189,7 +190,10 @@ extern __shared__ __align__(16) double cb_dyn_smem[];
 __shared__ double cb_red[34];
 __shared__ __align__(8) unsigned long long cb_bars[2];
 __shared__ unsigned cb_bar_uses;
-__shared__ long long cb_prof[32];      // phase counters of this CTA, flushed to the instance's slots when the kernel ends
+__shared__ long long cb_prof[32];
+#define CB_MAX_CHAIN 64
+__shared__ int4 cb_chain[2 * CB_MAX_CHAIN];   // ChainDesc of the shared-memory supernodes (filled once per kernel)
+__shared__ int cb_chain_n;                     // number of valid entries (0: read descriptors from global memory)      // phase counters of this CTA, flushed to the instance's slots when the kernel ends
 #define CB_SCRATCH(ctx) (cb_dyn_smem)
 #define CB_RED(ctx) (cb_red)
 #else
@@ -903,9 +907,17 @@ CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward
         if (ph.mode == 2) {
             g(cta, ph.begin, ph.end, ph.ebegin, ph.eend);
         } else if (ph.mode == 1) {
-            for (int q = ph.begin; q < ph.end; q++) f(cta, P.order[q]);
+            for (int q = ph.begin; q < ph.end; q++) {
+                const int hint = q == ph.begin ? ph.first_big : -2;
+#if CB_ON_DEVICE
+                const int s = (hint >= 0 && hint < cb_chain_n) ? cb_chain[2 * hint].x : P.order[q];
+#else
+                const int s = P.order[q];
+#endif
+                f(cta, s, hint);
+            }
         } else {
-            for (int q = ph.begin + CB_WARP_ID; q < ph.end; q += CB_NUM_WARPS) f(wctx, P.order[q]);
+            for (int q = ph.begin + CB_WARP_ID; q < ph.end; q += CB_NUM_WARPS) f(wctx, P.order[q], -1);
         }
         CB_CTA_SYNC();
         phase_end(forward ? pi : P.nphases - 1 - pi, ph.mode);
@@ -930,8 +942,8 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
     pt.stop(PROF_ASSEMBLE);
     for_each_supernode(
         ctx, P, true,
-        [&](const Ctx &c, int s) {
-            const int bi = (c.warp_scope || !P.big_index) ? -1 : P.big_index[s];
+        [&](const Ctx &c, int s, int hint) {
+            const int bi = (c.warp_scope || !P.big_index) ? -1 : (hint != -2 ? hint : P.big_index[s]);
             if (bi >= 0) {
                 factor_supernode_big(c, P, pan, D, Dinv, K, s, P.big[bi], pt);
             } else {
@@ -1086,14 +1098,21 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     ps.stop(PROF_SF_BULK);
     for_each_supernode(
         ctx, P, true,
-        [&](const Ctx &c, int s) {
+        [&](const Ctx &c, int s, int hint) {
             const Ctx &ctx = c;
-            const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
-            const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
-            const int bi = c.warp_scope ? -1 : P.big_index[s];
+            const int bi = c.warp_scope ? -1 : (hint != -2 ? hint : P.big_index[s]);
+            int c0, w, nR, rows_off, h1 = 0;
+            if (bi >= 0 && bi < cb_chain_n) {        // descriptor from shared memory: no global-memory chase
+                const int4 d0 = cb_chain[2 * bi], d1 = cb_chain[2 * bi + 1];
+                c0 = d0.y; w = d0.z; nR = d0.w; rows_off = d1.x; h1 = d1.z;
+            } else {
+                c0 = P.sn_start[s]; w = P.sn_start[s + 1] - c0;
+                rows_off = P.rows_ptr[s]; nR = P.rows_ptr[s + 1] - rows_off;
+                if (bi >= 0) h1 = P.big[bi].h1;
+            }
+            const int nrow = w + nR;
             if (bi >= 0) {
-                const int h1 = P.big[bi].h1;
-                const int *__restrict__ R = P.rows + P.rows_ptr[s];
+                const int *__restrict__ R = P.rows + rows_off;
                 // (contributions of the small descendants were pulled in bulk after their phases)
                 const int rI = (tid >> 2) < nR ? R[tid >> 2] : 0;      // row index of this thread's push row, in flight early
                 double y0 = 0.0, y1 = 0.0;      // warp 0: unknowns lane, lane + 32 (w <= 64)
@@ -1188,14 +1207,21 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     issue();
     for_each_supernode(
         ctx, P, false,
-        [&](const Ctx &c, int s) {
+        [&](const Ctx &c, int s, int hint) {
             const Ctx &ctx = c;
-            const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
-            const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;
-            const int *__restrict__ R = P.rows + P.rows_ptr[s];
-            const int bi = c.warp_scope ? -1 : P.big_index[s];
+            const int bi = c.warp_scope ? -1 : (hint != -2 ? hint : P.big_index[s]);
+            int c0, w, nR, rows_off, h1 = 0;
+            if (bi >= 0 && bi < cb_chain_n) {
+                const int4 d0 = cb_chain[2 * bi], d1 = cb_chain[2 * bi + 1];
+                c0 = d0.y; w = d0.z; nR = d0.w; rows_off = d1.x; h1 = d1.z;
+            } else {
+                c0 = P.sn_start[s]; w = P.sn_start[s + 1] - c0;
+                rows_off = P.rows_ptr[s]; nR = P.rows_ptr[s + 1] - rows_off;
+                if (bi >= 0) h1 = P.big[bi].h1;
+            }
+            const int nrow = w + nR;
+            const int *__restrict__ R = P.rows + rows_off;
             if (bi >= 0) {
-                const int h1 = P.big[bi].h1;
                 double z0 = 0.0, z1 = 0.0;      // warp 0: unknowns lane, lane + 32
                 if (wid == 0) { z0 = lane < w ? xs[c0 + lane] : 0.0; z1 = lane + 32 < w ? xs[c0 + lane + 32] : 0.0; }
                 for (int i = tid; i < nR; i += nthr) xr[i] = xs[R[i]];      // x[R] (final), staged once for both parts
@@ -1342,7 +1368,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
     // forward: pull from descendants through the per-column row lists, then the unit-lower diagonal block
     for_each_supernode(
         ctx, P, true,
-        [&](const Ctx &c, int s) {
+        [&](const Ctx &c, int s, int hint) {
             const Ctx &ctx = c;
             const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
             const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
@@ -1381,7 +1407,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
     // backward: gather from the ancestors' (already final) entries, then the unit-upper diagonal block
     for_each_supernode(
         ctx, P, false,
-        [&](const Ctx &c, int s) {
+        [&](const Ctx &c, int s, int hint) {
             const Ctx &ctx = c;
             const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
             const int nR = P.rows_ptr[s + 1] - P.rows_ptr[s], nrow = w + nR;

@@ -361,7 +361,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         while (j < ns && level[order[j]] == level[order[i]] && cls[order[j]] == cls[order[i]]) j++;
         int mode = cls[order[i]] == 0 ? 2 : (cls[order[i]] == 1 ? 1 : 0);
         if (mode == 0 && j - i == 1) mode = 1;  // a lone small task: let the whole CTA help anyway
-        phases.push_back(Phase{mode, i, j, 0, 0});
+        phases.push_back(Phase{mode, i, j, 0, 0, -1});
         i = j;
     }
     // 6b. shared-memory staging plan for CTA-scope targets
@@ -443,6 +443,13 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>(ysize, aux) + 8);
         }
     }
+    bdesc.clear();
+    for (size_t bi = 0; bi < big.size(); bi++) {
+        const int t = big_seq[bi];
+        bdesc.push_back(ChainDesc{t, sn_start[t], sn_start[t + 1] - sn_start[t], rows_ptr[t + 1] - rows_ptr[t], rows_ptr[t],
+                                  (int)panel_off[t], big[bi].h1, 0});
+    }
+    for (Phase &ph : phases) ph.first_big = ph.mode == 1 ? big_index[order[ph.begin]] : -1;
     big_seq_bwd.clear();
     for (int pi = (int)phases.size() - 1; pi >= 0; pi--)
         if (phases[pi].mode == 1)

@@ -23,6 +23,14 @@ struct Phase {
                      // 2: singleton leaves (width 1, no incoming update), one thread per supernode
     int begin, end;  // range in Symbolic::order
     int ebegin, eend; // mode 2: range in the flat leaf-entry lists (leaf_e_off / leaf_e_col / leaf_e_pos)
+    int first_big;   // mode 1: index in big[] of the phase's first task (-1: not on the shared-memory path)
+};
+
+// What the numeric phases need to know about a shared-memory supernode, 32 bytes: kept in shared memory for the whole
+// kernel so that the chain steps of the solves do not chase sn_start / rows_ptr / big_index / big through global memory.
+struct ChainDesc {
+    int s, c0, w, nR;
+    int rows_off, panel_off, h1, pad;
 };
 
 // A CTA-scope target whose panel fits in shared memory pulls ALL its descendants' columns at once: they are staged
@@ -110,6 +118,7 @@ struct Symbolic {
     // shared-memory path for big targets
     std::vector<int> big_index;   // [ns] index into big, or -1
     std::vector<BigTarget> big;
+    std::vector<ChainDesc> bdesc; // [big.size()]
     std::vector<YChunk> ychunks;
     std::vector<int> ystage_src, ystage_dst, ypiv;
     std::vector<unsigned> ymask;

@@ -30,7 +30,7 @@ struct Batch {
     int count, F;
     long long ksize;
     double *w, *cand, *step, *res, *err, *corr, *tmp;
-    double *grad, *gyx, *hzx, *g, *h, *Wv, *Gv, *Cv, *prod, *bgrad, *lambda;
+    double *grad, *gyx, *hzx, *g, *h, *Wv, *Gv, *Cv, *Wf, *Gr, *prod, *bgrad, *lambda;
     double *panels, *D, *Dinv, *kx, *Lcsr, *xs, *rs, *xp, *mgrad, *q, *g0, *h0, *filter, *krylov, *scal;
     double *Aval, *rhs;
     int *istat;
@@ -45,6 +45,7 @@ struct Batch {
         I.grad = grad + b * n; I.gyx = gyx + b * n; I.hzx = hzx + b * n;
         I.g = g + b * m; I.h = h + b * p;
         I.Wv = Wv + b * (long long)P.nnzW; I.Gv = Gv + b * (long long)P.nnzG; I.Cv = Cv + b * (long long)P.nnzC;
+        I.Wf = Wf + b * (long long)P.nnzWf; I.Gr = Gr + b * (long long)P.nnzG;
         I.prod = prod + b * p; I.bgrad = bgrad + b * p; I.lambda = lambda + b * m;
         I.panels = panels + b * P.panel_total; I.D = D + b * N; I.Dinv = Dinv + b * N;
         I.kx = kx + b * P.kx_total;
@@ -83,6 +84,12 @@ struct Batch {
     const int b = blockIdx.x;                             \
     if (b >= B.count) return;                             \
     Inst I = B.inst(P, b);
+
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_expand(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+{
+    KERNEL_PROLOGUE
+    expand_values(ctx, P, I);
+}
 
 __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_cone(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int flags, int at_candidate)
 {
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(co
     pt.start();
     kkt_entries(ctx, P, I);
     pt.stop(PROF_ASSEMBLE);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gr, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
     for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
     PROF_FLUSH(I.prof);
 }
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_differentiate(const
 {
     KERNEL_PROLOGUE
     kkt_entries(ctx, P, I);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gr, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
     for (int i = 0; i < nparam; i++) {
         const double *rhs = H + ((long long)b * nparam + i) * P.total;
         double *out = S + ((long long)b * nparam + i) * P.total;
@@ -266,6 +273,7 @@ struct cb200_handle {
     void *comm = nullptr;
     int nranks = 1;
     int nnzW = 0, nnzG = 0, nnzC = 0;
+    bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
 };
 
 extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
@@ -375,6 +383,7 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
     B.grad = dalloc(h, n, ok); B.gyx = dalloc(h, n, ok); B.hzx = dalloc(h, n, ok);
     B.g = dalloc(h, m, ok); B.h = dalloc(h, p, ok);
     B.Wv = dalloc(h, nnzW, ok); B.Gv = dalloc(h, nnzG, ok); B.Cv = dalloc(h, nnzC, ok);
+    B.Wf = dalloc(h, P.nnzWf, ok); B.Gr = dalloc(h, nnzG, ok);
     B.prod = dalloc(h, p, ok); B.bgrad = dalloc(h, p, ok); B.lambda = dalloc(h, m, ok);
     B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);
     B.kx = dalloc(h, P.kx_total, ok); B.Lcsr = dalloc(h, P.lcsr_total, ok);
@@ -506,6 +515,7 @@ extern "C" int cb200_set_array(cb200_handle *h, int which, const double *host, i
     CUDA_OK(cudaSetDevice(h->device));
     const ArrayDesc &a = h->arr[which];
     CUDA_OK(cudaMemcpyAsync(a.ptr + (long long)first * a.len, host, sizeof(double) * a.len * count, cudaMemcpyHostToDevice, h->stream));
+    if (which == CB200_W_VALUES || which == CB200_G_VALUES) h->values_dirty = true;
     return 0;
 }
 
@@ -586,26 +596,36 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
         CUDA_OK(cudaGetLastError());                                                                      \
     } while (0)
 #define NEED_KKT() if (h->generic) return fail("not available on a LinearSolver-seam handle")
+// kernels that read the row-ordered copies of W / G refresh them first when cb200_set_array changed the values
+#define FRESH_VALUES()                                          \
+    do {                                                        \
+        if (h->values_dirty) {                                  \
+            LAUNCH(k_expand, h->P, h->B);                       \
+            h->values_dirty = false;                            \
+        }                                                       \
+    } while (0)
 
 extern "C" int cb200_cone(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); LAUNCH(k_cone, h->P, h->B, flags, at_candidate); return 0; }
 extern "C" int cb200_residual(cb200_handle *h) { NEED_KKT(); LAUNCH(k_residual, h->P, h->B); return 0; }
-extern "C" int cb200_search_direction(cb200_handle *h) { NEED_KKT(); LAUNCH_SMEM(k_search_direction, h->P, h->B, h->opt); return 0; }
+extern "C" int cb200_search_direction(cb200_handle *h) { NEED_KKT(); FRESH_VALUES(); LAUNCH_SMEM(k_search_direction, h->P, h->B, h->opt); return 0; }
 extern "C" int cb200_cone_search(cb200_handle *h) { NEED_KKT(); LAUNCH(k_cone_search, h->P, h->B, h->opt); return 0; }
 extern "C" int cb200_apply_step(cb200_handle *h) { NEED_KKT(); LAUNCH(k_apply_step, h->P, h->B); return 0; }
-extern "C" int cb200_lq_evaluate(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); LAUNCH(k_lq_evaluate, h->P, h->B, flags, at_candidate); return 0; }
-extern "C" int cb200_lq_begin(cb200_handle *h, int warmstart) { NEED_KKT(); LAUNCH(k_lq_begin, h->P, h->B, h->opt, warmstart); return 0; }
+extern "C" int cb200_lq_evaluate(cb200_handle *h, int flags, int at_candidate) { NEED_KKT(); FRESH_VALUES(); LAUNCH(k_lq_evaluate, h->P, h->B, flags, at_candidate); return 0; }
+extern "C" int cb200_lq_begin(cb200_handle *h, int warmstart) { NEED_KKT(); FRESH_VALUES(); LAUNCH(k_lq_begin, h->P, h->B, h->opt, warmstart); return 0; }
 extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
 {
     NEED_KKT();
+    FRESH_VALUES();
     for (int k = 0; k < iterations; k++) LAUNCH_SMEM(k_lq_step, h->P, h->B, h->opt);
     return 0;
 }
-extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); LAUNCH_SMEM(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
+extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); FRESH_VALUES(); LAUNCH_SMEM(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
 
 extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_host, double *S_host)
 {
     NEED_KKT();
     if (nparam <= 0) return 0;
+    FRESH_VALUES();
     CUDA_OK(cudaSetDevice(h->device));
     const size_t bytes = sizeof(double) * (size_t)h->batch * (size_t)nparam * (size_t)h->P.total;
     double *dH = nullptr, *dS = nullptr;
@@ -633,6 +653,7 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host)
 {
     NEED_KKT();
+    FRESH_VALUES();
     CUDA_OK(cudaSetDevice(h->device));
     size_t bytes = sizeof(double) * h->P.total * (size_t)h->batch;
     CUDA_OK(cudaMemcpyAsync(h->B.err, v_host, bytes, cudaMemcpyHostToDevice, h->stream));

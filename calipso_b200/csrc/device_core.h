@@ -44,7 +44,7 @@ struct Csr {          // row-wise view of a CSC matrix: entry k of row i is valu
 struct DevProblem {   // everything shared by the instances of a batch (device pointers)
     int n, m, p, N, total;
     int q_nn, nsoc, tri_total;
-    int nnzW, nnzG, nnzC;
+    int nnzW, nnzG, nnzC, nnzWf;               // nnzWf: entries of the symmetric W by rows (both triangles)
     const int *soc_off, *soc_dims, *soc_tri;  // soc_tri[k]: offset of cone k's upper-triangle entries in dZsoc
     // patterns
     const int *Wp, *Wi, *Wdiag;               // upper triangle CSC, Wdiag[j] = position of (j,j)
@@ -141,6 +141,7 @@ struct Inst {         // device pointers of ONE instance
     double *grad, *gyx, *hzx;                          // [n]
     double *g, *h;                                     // [m], [p]
     double *Wv, *Gv, *Cv;                              // values at the patterns
+    double *Wf, *Gr;                                   // row-ordered copies (expand_values): symmetric W by rows, G by rows
     double *prod, *bgrad;                              // [p]
     double *lambda;                                    // [m]
     double *panels, *D, *Dinv, *kx, *Lcsr;           // factor (+ M blocks of the big supernodes, leaf CSR copy)
@@ -427,6 +428,16 @@ CB_DEV void merit_gradient(const Ctx &ctx, const DevProblem &P, const Inst &I)
 }
 
 // ------------------------------------------------------------------------------------------------ KKT assembly
+// Row-ordered copies of the callback outputs, refreshed whenever W or G values change: Wf = symmetric W by rows (both
+// triangles), Gr = G by rows.  Every row-wise consumer (J v, the LQ callbacks, the multiplier leaves of the
+// factorisation, whose columns are rows of G) then reads contiguous values instead of gathering through the CSC storage.
+CB_DEVN void expand_values(const Ctx &ctx, const DevProblem &P, const Inst &I)
+{
+    PAR_FOR(k, P.nnzWf) I.Wf[k] = I.Wv[P.Wfull.src[k]];
+    PAR_FOR(k, P.nnzG) I.Gr[k] = I.Gv[P.Grow.src[k]];
+    ctx.sync();
+}
+
 // The entries of the reduced matrix K that are not plain copies of W, G, C values:
 // kx = [W diagonal + eps_p | y diagonal | nonnegative z diagonal | upper triangles of the second-order z blocks].
 // eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.  The matrix itself
@@ -1552,10 +1563,10 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
     const double *vx = v, *vr = v + n, *vs = v + n + m, *vy = v + n + m + p, *vz = v + n + 2 * m + p,
                  *vt = v + n + 2 * m + 2 * p;
     {
-        const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col, *__restrict__ ws = P.Wfull.src;
+        const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col;
         const int *__restrict__ gp = P.Gp, *__restrict__ gi = P.Gi, *__restrict__ cp = P.Cp, *__restrict__ ci = P.Ci;
-        const double *__restrict__ Wv = I.Wv, *__restrict__ Gv = I.Gv, *__restrict__ Cv = I.Cv;
-        const int *__restrict__ grp = P.Grow.ptr, *__restrict__ grc = P.Grow.col, *__restrict__ grs = P.Grow.src;
+        const double *__restrict__ Gv = I.Gv, *__restrict__ Cv = I.Cv;
+        const int *__restrict__ grp = P.Grow.ptr, *__restrict__ grc = P.Grow.col;
 #if CB_ON_DEVICE
         unsigned dyn_bytes;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
@@ -1578,7 +1589,7 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
                     const bool okn = in < n;
                     const int nw0 = okn ? wp[in] : 0, nw1 = okn ? wp[in + 1] : 0, ng0 = okn ? gp[in] : 0,
                               ng1 = okn ? gp[in + 1] : 0, nc0 = okn ? cp[in] : 0, nc1 = okn ? cp[in + 1] : 0;
-                    double a = sparse_dot4(Wv, ws, wc, sx, w0, w1, sub) + sparse_dot4(Gv, nullptr, gi, sy, g0, g1, sub);
+                    double a = sparse_dot4(I.Wf, nullptr, wc, sx, w0, w1, sub) + sparse_dot4(Gv, nullptr, gi, sy, g0, g1, sub);
                     for (int k = c0 + sub; k < c1; k += 4) a += Cv[k] * sz[ci[k]];
                     a += __shfl_xor_sync(0xffffffffu, a, 1);
                     a += __shfl_xor_sync(0xffffffffu, a, 2);
@@ -1593,7 +1604,7 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
                 for (; i < padded; i += ngrp) {
                     const int in = i + ngrp;
                     const int na0 = in < m ? P.Grow.ptr[in] : 0, na1 = in < m ? P.Grow.ptr[in + 1] : 0;
-                    double a = sparse_dot4(Gv, grs, grc, sx, a0, a1, sub);
+                    double a = sparse_dot4(I.Gr, nullptr, grc, sx, a0, a1, sub);
                     a += __shfl_xor_sync(0xffffffffu, a, 1);
                     a += __shfl_xor_sync(0xffffffffu, a, 2);
                     if (sub == 0 && i < m) {
@@ -1611,7 +1622,7 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
                 ctx, n,
                 [&](int i, int sub, int st) {
                     double a = 0.0;
-                    for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += Wv[ws[k]] * vx[wc[k]];
+                    for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += I.Wf[k] * vx[wc[k]];
                     for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += Gv[k] * vy[gi[k]];
                     for (int k = cp[i] + sub; k < cp[i + 1]; k += st) a += Cv[k] * vz[ci[k]];
                     return a;
@@ -1621,7 +1632,7 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
                 ctx, m,
                 [&](int i, int sub, int st) {
                     double a = 0.0;
-                    for (int k = grp[i] + sub; k < grp[i + 1]; k += st) a += Gv[grs[k]] * vx[grc[k]];
+                    for (int k = grp[i] + sub; k < grp[i + 1]; k += st) a += I.Gr[k] * vx[grc[k]];
                     return a;
                 },
                 [&](int i, double a) {
@@ -1656,7 +1667,7 @@ CB_DEV bool factorize_regularized(const Ctx &ctx, const DevProblem &P, const Ins
     pt.start();
     kkt_entries(ctx, P, I);
     pt.stop(PROF_ASSEMBLE);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
+    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gr, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
     bool ok = I.istat[I_INERTIA_POS] == P.n && I.istat[I_INERTIA_NEG] == P.m + P.p && I.istat[I_INERTIA_ZERO] == 0;
     ctx.sync();
     if (ctx.tid == 0) I.istat[I_TRIALS]++;

@@ -20,14 +20,13 @@ CB_DEVN void lq_evaluate(const Ctx &ctx, const DevProblem &P, const Inst &I, con
     const double *x = w, *y = w + n + m + p, *z = w + n + 2 * m + p;
     // sparse rows by groups of four lanes (grouped_rows): short dependent-load chains, coalesced index reads
     if (flags & (EV_OBJECTIVE | EV_GRADIENT)) {
-        const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col, *__restrict__ ws = P.Wfull.src;
-        const double *__restrict__ Wv = I.Wv;
+        const int *__restrict__ wp = P.Wfull.ptr, *__restrict__ wc = P.Wfull.col;
         double *red = I.tmp;       // per-row terms of the objective (summed below in a fixed order)
         grouped_rows<4>(
             ctx, n,
             [&](int i, int sub, int st) {
                 double a = 0.0;
-                for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += Wv[ws[k]] * x[wc[k]];
+                for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += I.Wf[k] * x[wc[k]];
                 return a;
             },
             [&](int i, double a) {
@@ -41,13 +40,12 @@ CB_DEVN void lq_evaluate(const Ctx &ctx, const DevProblem &P, const Inst &I, con
         }
     }
     if (flags & EV_EQUALITY) {
-        const int *__restrict__ gp = P.Grow.ptr, *__restrict__ gc = P.Grow.col, *__restrict__ gs = P.Grow.src;
-        const double *__restrict__ Gv = I.Gv;
+        const int *__restrict__ gp = P.Grow.ptr, *__restrict__ gc = P.Grow.col;
         grouped_rows<4>(
             ctx, m,
             [&](int i, int sub, int st) {
                 double a = 0.0;
-                for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += Gv[gs[k]] * x[gc[k]];
+                for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += I.Gr[k] * x[gc[k]];
                 return a;
             },
             [&](int i, double a) { I.g[i] = I.g0[i] + a; });

@@ -124,7 +124,11 @@ struct HostProblem {
             std::vector<int> code(Ki.size(), -1);
             for (int k = 0; k < nnzW; k++) code[eW[k]] = k;
             for (int j = 0; j < n; j++) code[eW[Wdiag[j]]] = (int)((3u << 30) | (unsigned)j);
-            for (int k = 0; k < nnzG; k++) code[eG[k]] = (1 << 30) | k;
+            {   // G values are read from the row-ordered copy Gr: position of CSC entry k in the row view
+                std::vector<int> rowpos(nnzG);
+                for (int r = 0; r < nnzG; r++) rowpos[Gsrc[r]] = r;
+                for (int k = 0; k < nnzG; k++) code[eG[k]] = (1 << 30) | rowpos[k];
+            }
             for (int k = 0; k < nnzC; k++) code[eC[k]] = (int)((2u << 30) | (unsigned)k);
             for (int i = 0; i < m; i++) code[eY[i]] = (int)((3u << 30) | (unsigned)(n + i));
             for (int i = 0; i < q_nn; i++) code[eZnn[i]] = (int)((3u << 30) | (unsigned)(n + m + i));
@@ -190,7 +194,7 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
 template <class Up> void fill_problem(DevProblem &P, const HostProblem &H, Up up)
 {
     P.n = H.n; P.m = H.m; P.p = H.p; P.total = H.total; P.q_nn = H.q_nn; P.nsoc = H.nsoc; P.tri_total = H.tri_total;
-    P.nnzW = H.nnzW; P.nnzG = H.nnzG; P.nnzC = H.nnzC;
+    P.nnzW = H.nnzW; P.nnzG = H.nnzG; P.nnzC = H.nnzC; P.nnzWf = (int)H.Wfc.size();
     fill_symbolic(P, H.sym, up);
     P.soc_off = up(H.soc_off); P.soc_dims = up(H.soc_d); P.soc_tri = up(H.soc_tri);
     P.Wp = up(H.Wp); P.Wi = up(H.Wi); P.Wdiag = up(H.Wdiag);

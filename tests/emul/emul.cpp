@@ -31,7 +31,7 @@ struct cb200_handle {
     const Symbolic &sym() const { return generic ? gsym : hp.sym; }
 };
 
-enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_KX, X_LCSR, X_COUNT };
+enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_KX, X_LCSR, X_WF, X_GR, X_COUNT };
 
 extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
 extern "C" int cb200_device_count(void) { return 0; }
@@ -71,6 +71,7 @@ static Inst inst(cb200_handle *h, int b)
     I.Wv = at(CB200_W_VALUES); I.Gv = at(CB200_G_VALUES); I.Cv = at(CB200_C_VALUES);
     I.prod = at(CB200_CONE_PRODUCT); I.bgrad = at(CB200_BARRIER_GRADIENT); I.lambda = at(CB200_DUAL);
     I.panels = at(CB200_PANELS); I.D = at(CB200_PIVOTS); I.Dinv = at(X_DINV); I.kx = at(X_KX); I.Lcsr = at(X_LCSR); I.prof = nullptr;
+    I.Wf = at(X_WF); I.Gr = at(X_GR);
     I.xs = at(CB200_STEP_SYMMETRIC); I.rs = at(CB200_RESIDUAL_SYMMETRIC); I.xp = at(X_XP);
     I.mgrad = at(CB200_MERIT_GRADIENT); I.q = at(CB200_LQ_Q); I.g0 = at(CB200_LQ_G0); I.h0 = at(CB200_LQ_H0);
     I.filter = at(X_FILTER); I.krylov = h->ksize ? at(X_KRYLOV) : nullptr;
@@ -107,6 +108,7 @@ extern "C" cb200_handle *cb200_create(int batch, int n, int m, int p, int q_nn, 
     for (int w : {(int)CB200_MERIT_GRADIENT, (int)CB200_RESIDUAL_SYMMETRIC, (int)CB200_STEP_SYMMETRIC, (int)CB200_PIVOTS, (int)X_DINV, (int)X_XP}) alloc(h, w, N);
     alloc(h, CB200_PANELS, P.panel_total);
     alloc(h, X_KX, P.kx_total);
+    alloc(h, X_WF, P.nnzWf); alloc(h, X_GR, P.nnzG);
     alloc(h, X_LCSR, P.lcsr_total);
     h->scratch.assign((size_t)h->hp.sym.scratch_doubles + 8, 0.0);
     alloc(h, X_FILTER, 4LL * h->opt.max_filter);
@@ -219,12 +221,18 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
 }
 
 static double g_red[34];
+static void refresh_values(cb200_handle *h);
 #define FOR_EACH_INSTANCE                       \
     Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr}; \
     const DevProblem &P = h->P;                 \
     for (int b = 0; b < h->batch; b++) {        \
         Inst I = inst(h, b);
 #define END_FOR }
+static void refresh_values(cb200_handle *h)
+{   // (the CUDA library does this only when cb200_set_array changed W or G values; here: always)
+    if (h->generic) return;
+    FOR_EACH_INSTANCE expand_values(ctx, P, I); END_FOR
+}
 
 extern "C" int cb200_cone(cb200_handle *h, int flags, int at_candidate)
 {
@@ -238,6 +246,7 @@ extern "C" int cb200_residual(cb200_handle *h)
 }
 extern "C" int cb200_search_direction(cb200_handle *h)
 {
+    refresh_values(h);
     FOR_EACH_INSTANCE I.istat[I_STATUS] = search_direction(ctx, P, I, h->opt); END_FOR
     return 0;
 }
@@ -267,18 +276,20 @@ extern "C" int cb200_apply_step(cb200_handle *h)
 }
 extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves)
 {
+    refresh_values(h);
     FOR_EACH_INSTANCE
         kkt_entries(ctx, P, I);
-        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, nullptr);
+        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gr, I.Cv, I.kx}, I.Lcsr, I.istat, nullptr);
         for (int k = 0; k < nsolves; k++) direction_symmetric(ctx, P, I, I.res, I.step);
     END_FOR
     return 0;
 }
 extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H, double *S)
 {
+    refresh_values(h);
     FOR_EACH_INSTANCE
         kkt_entries(ctx, P, I);
-        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gv, I.Cv, I.kx}, I.Lcsr, I.istat, nullptr);
+        ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gr, I.Cv, I.kx}, I.Lcsr, I.istat, nullptr);
         for (int i = 0; i < nparam; i++) {
             const double *rhs = H + ((long long)b * nparam + i) * P.total;
             double *out = S + ((long long)b * nparam + i) * P.total;
@@ -290,21 +301,25 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H,
 }
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v, double *out)
 {
+    refresh_values(h);
     FOR_EACH_INSTANCE jacobian_times(ctx, P, I, v + (long long)b * P.total, out + (long long)b * P.total); END_FOR
     return 0;
 }
 extern "C" int cb200_lq_evaluate(cb200_handle *h, int flags, int at_candidate)
 {
+    refresh_values(h);
     FOR_EACH_INSTANCE lq_evaluate(ctx, P, I, at_candidate ? I.cand : I.w, flags); END_FOR
     return 0;
 }
 extern "C" int cb200_lq_begin(cb200_handle *h, int warmstart)
 {
+    refresh_values(h);
     FOR_EACH_INSTANCE solve_begin_lq(ctx, P, I, h->opt, warmstart); END_FOR
     return 0;
 }
 extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
 {
+    refresh_values(h);
     for (int k = 0; k < iterations; k++) { FOR_EACH_INSTANCE solve_step_lq(ctx, P, I, h->opt); END_FOR }
     return 0;
 }

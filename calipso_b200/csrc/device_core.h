@@ -80,6 +80,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const YChunk *ychunks;
     const int *ystage_src, *ystage_dst, *ypiv;
     const unsigned *ymask;
+    const int *dg_dst, *dg_ptr, *dg_src, *dg_piv;   // diagonal updates from single-entry descendant columns
     long long kx_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
     int nbig, max_sb_doubles, solve_smem;
@@ -857,6 +858,18 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
 #endif
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_GEMM);
+    }
+    {   // descendant columns with a single entry in this target: S[r, r] -= sum l^2 d (grouped by destination)
+        const int ng = bt.dg_end - bt.dg_begin;
+        PAR_FOR(g, ng) {
+            double acc = 0.0;
+            for (int e = P.dg_ptr[bt.dg_begin + g]; e < P.dg_ptr[bt.dg_begin + g + 1]; e++) {
+                const double l = pan[P.dg_src[e]];
+                acc += l * (l * D[P.dg_piv[e]]);
+            }
+            S[P.dg_dst[bt.dg_begin + g]] -= acc;
+        }
+        if (ng > 0) ctx.sync();
     }
     double *dd = Y + 72;                 // w pivots
 #if CB_ON_DEVICE

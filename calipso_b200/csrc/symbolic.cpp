@@ -367,6 +367,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     // 6b. shared-memory staging plan for CTA-scope targets
     big_index.assign(ns, -1);
     big.clear(); ychunks.clear(); ystage_src.clear(); ystage_dst.clear(); ypiv.clear(); ymask.clear(); big_seq.clear();
+    dg_dst.clear(); dg_src.clear(); dg_piv.clear(); dg_ptr.assign(1, 0);
     max_sb_doubles = 0;
     kx_total = 0;
     scratch_doubles = 0;
@@ -412,10 +413,18 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                 max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
                 ychunks.push_back(ch);
             };
+            std::vector<std::pair<int, std::pair<int, int>>> singles;   // (local row, (panel offset, pivot column))
             for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) {
                 const UpdateEntry &ue = upd[u];
                 int cd0 = sn_start[ue.d], wd = sn_start[ue.d + 1] - cd0;
                 int nRd = rows_ptr[ue.d + 1] - rows_ptr[ue.d], nrowd = wd + nRd;
+                if (nRd - ue.a == 1) {      // one row only: a diagonal update (or nothing, if the row is below the pivots)
+                    const int lrow = rel[ue.rel];
+                    if (lrow < w)
+                        for (int k = 0; k < wd; k++)
+                            singles.push_back({lrow, {(int)(panel_off[ue.d] + (wd + ue.a) + (long long)k * nrowd), cd0 + k}});
+                    continue;
+                }
                 for (int k = 0; k < wd; k++) {
                     if (col - ch.col_begin == kc_max) {   // chunk full
                         close_chunk();
@@ -432,6 +441,17 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                     col++;
                 }
             }
+            std::stable_sort(singles.begin(), singles.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+            bt.dg_begin = (int)dg_dst.size();
+            for (size_t i = 0; i < singles.size();) {
+                size_t j = i;
+                while (j < singles.size() && singles[j].first == singles[i].first) j++;
+                dg_dst.push_back(singles[i].first * (ldp + 1));
+                for (size_t e = i; e < j; e++) { dg_src.push_back(singles[e].second.first); dg_piv.push_back(singles[e].second.second); }
+                dg_ptr.push_back((int)dg_src.size());
+                i = j;
+            }
+            bt.dg_end = (int)dg_dst.size();
             if (col > ch.col_begin) close_chunk();
             else ymask.resize(ch.mask_begin);
             bt.chunk_end = (int)ychunks.size();

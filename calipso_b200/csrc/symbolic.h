@@ -50,6 +50,7 @@ struct BigTarget {
     int ldp;                     // leading dimension of the panel work area (same rounding)
     int panel_doubles;           // size of the supernode's panel in the factor storage (even): one TMA bulk copy in the solves
     int asm_begin, asm_end;      // range in basm_src / basm_dst: the input entries of this supernode (fused assembly)
+    int dg_begin, dg_end;        // range of diagonal-update groups (descendant columns with a single entry in this target)
     int h1;                      // the solves stream the panel in one part (h1 == w) or two: columns [0, h1) and [h1, w)
 };
 struct FwdEntry {                // one (descendant, row) pair of the forward-solve row lists, flattened
@@ -122,6 +123,10 @@ struct Symbolic {
     std::vector<YChunk> ychunks;
     std::vector<int> ystage_src, ystage_dst, ypiv;
     std::vector<unsigned> ymask;
+    // descendant columns whose only entry in a target is one row r: they never enter Y; S[r, r] -= sum l^2 d per
+    // destination group (r < w), fixed order
+    std::vector<int> dg_dst, dg_ptr;          // per group: offset in the work area S; [groups + 1] range in dg_src / dg_piv
+    std::vector<int> dg_src, dg_piv;          // per entry: panel offset of l, pivot column of d
     std::vector<int> big_seq;     // shared-memory supernodes in forward schedule order (TMA prefetch chain)
     std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
     std::vector<int> parts_fwd, parts_bwd;   // TMA copies of the solves in issue order: (panel offset, doubles) pairs

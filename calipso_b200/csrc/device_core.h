@@ -80,6 +80,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     const YChunk *ychunks;
     const int *ystage_src, *ystage_dst, *ypiv;
     const unsigned *ymask;
+    const int *yb_row, *yb_ptr, *yb_col;       // below-pivot entries of the staged columns, grouped by target row
     const int *dg_dst, *dg_ptr, *dg_src, *dg_piv;   // diagonal updates from single-entry descendant columns
     long long kx_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
@@ -810,7 +811,7 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
 #if CB_ON_DEVICE
         {   // S[i, j] -= sum_c Y[i, c] Dy[c] Y[j, c] for the 8x8 tiles that touch the lower triangle
             const int gid = lane >> 2, tig = lane & 3;
-            const int ntI = (nrow + 7) >> 3, ntJ = (w + 7) >> 3;
+            const int ntI = (w + 7) >> 3, ntJ = ntI;          // Y holds the pivot rows only
             const unsigned *__restrict__ msk = P.ymask + ch.mask_begin;
             const bool wide = ntI > 32;                                // (then the masks are read from memory per tile)
             const unsigned mymask = lane < ntI ? msk[lane] : 0u;
@@ -837,7 +838,7 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
                     }
                     if (g < g1) dmma_8x8x4(e0, e1, ya[0], yb[0] * dy[0]);
                     const int r = 8 * ti + gid, col = 8 * tj + 2 * tig;
-                    if (r < nrow) {
+                    if (r < w) {
                         if (col < w) S[r + col * ldp] -= e0 + f0;
                         if (col + 1 < w) S[r + (col + 1) * ldp] -= e1 + f1;
                     }
@@ -847,8 +848,8 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
             }
         }
 #else
-        PAR_FOR(e, nrow * w) {
-            const int j = e / nrow, i = e % nrow;
+        PAR_FOR(e, w * w) {
+            const int j = e / w, i = e % w;
             if (i >= j) {
                 double acc = 0.0;
                 for (int cc = 0; cc < kc; cc++) acc += Y[i + (long long)cc * ldy] * (Y[j + (long long)cc * ldy] * Dy[cc]);
@@ -856,6 +857,19 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
             }
         }
 #endif
+        {   // rows below the pivots: S[r, 0:w] -= sum_e l_e Dy[c_e] Y[0:w, c_e] (few entries; scalars staged after Dy)
+            const int ng = ch.bg_end - ch.bg_begin, e_first = P.yb_ptr[ch.bg_begin];
+            const double *Bl = Dy + kc4;
+            PAR_FOR(it, ng * w) {
+                const int g = it / w, j = it - g * w;
+                double acc = 0.0;
+                for (int e = P.yb_ptr[ch.bg_begin + g]; e < P.yb_ptr[ch.bg_begin + g + 1]; e++) {
+                    const int cc = P.yb_col[e];
+                    acc += (Bl[e - e_first] * Dy[cc]) * Y[j + (long long)cc * ldy];
+                }
+                S[P.yb_row[ch.bg_begin + g] + (long long)j * ldp] -= acc;
+            }
+        }
         ctx.sync();
         pt.stop(PROF_FACTOR_BIG_GEMM);
     }

@@ -174,6 +174,7 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.order = up(S.order); P.phases = up(S.phases); P.fwd_ptr = up(S.fwd_ptr); P.fwd = up(S.fwd);
     P.big_index = up(S.big_index); P.big = up(S.big); P.bdesc = up(S.bdesc); P.ychunks = up(S.ychunks);
     P.ystage_src = up(S.ystage_src); P.ystage_dst = up(S.ystage_dst); P.ypiv = up(S.ypiv); P.ymask = up(S.ymask);
+    P.yb_row = up(S.yb_row); P.yb_ptr = up(S.yb_ptr); P.yb_col = up(S.yb_col);
     P.dg_dst = up(S.dg_dst); P.dg_ptr = up(S.dg_ptr); P.dg_src = up(S.dg_src); P.dg_piv = up(S.dg_piv);
     P.kx_total = S.kx_total;
     P.big_seq = up(S.big_seq); P.big_seq_bwd = up(S.big_seq_bwd); P.nbig = (int)S.big_seq.size(); P.max_sb_doubles = S.max_sb_doubles;

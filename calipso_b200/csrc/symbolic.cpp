@@ -367,6 +367,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     // 6b. shared-memory staging plan for CTA-scope targets
     big_index.assign(ns, -1);
     big.clear(); ychunks.clear(); ystage_src.clear(); ystage_dst.clear(); ypiv.clear(); ymask.clear(); big_seq.clear();
+    yb_row.clear(); yb_col.clear(); yb_ptr.assign(1, 0);
     dg_dst.clear(); dg_src.clear(); dg_piv.clear(); dg_ptr.assign(1, 0);
     max_sb_doubles = 0;
     kx_total = 0;
@@ -376,19 +377,29 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         for (int q = ph.begin; q < ph.end; q++) {
             int t = order[q];
             int w = sn_start[t + 1] - sn_start[t], nrow = w + rows_ptr[t + 1] - rows_ptr[t];
-            const int ldy = ((nrow + 7) & ~7) + 4;
-            const int ldp = ((nrow + 7) & ~7) + 4;
-            const int ntI = (nrow + 7) / 8;
+            const int ldy = ((w + 7) & ~7) + 4;                           // Y holds the pivot rows only
+            const int ldp = nrow + ((4 - nrow % 8) + 8) % 8;              // smallest value >= nrow that is 4 mod 8
+            const int ntI = (w + 7) / 8;
+            const int bottom_reserve = 64;                               // (see the fit test below)                              // scalars of below-pivot entries per chunk
             const long long fixed = (long long)ldp * w;
             // after the GEMM the Y area is reused by the panel factorisation: 8x8 pivot block, 8 reciprocals, w pivots,
             // 8 x (w rounded + 4) unscaled multipliers
             const long long aux = 64 + 8 + w + 8LL * (((w + 7) & ~7) + 4) + 8;
             int ktot = 0;
-            for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) ktot += sn_start[upd[u].d + 1] - sn_start[upd[u].d];
-            if (fixed + std::max<long long>(ktot > 0 ? (long long)(ldy + 1) * 8 : 0, aux) > smem_budget_doubles) continue;   // generic path
+            bool bottoms_fit = true;
+            for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) {
+                const UpdateEntry &ue = upd[u];
+                const int nRd = rows_ptr[ue.d + 1] - rows_ptr[ue.d];
+                ktot += sn_start[ue.d + 1] - sn_start[ue.d];
+                int nb = 0;
+                for (int i = ue.a; i < nRd; i++) nb += rel[ue.rel + (i - ue.a)] >= w;
+                if (nb > bottom_reserve) bottoms_fit = false;
+            }
+            if (!bottoms_fit) continue;                                  // generic path
+            if (fixed + std::max<long long>(ktot > 0 ? (long long)(ldy + 1) * 8 + bottom_reserve : 0, aux) > smem_budget_doubles) continue;   // generic path
             int kc_max = 0;
             if (ktot > 0) {
-                kc_max = (int)std::min<long long>((smem_budget_doubles - fixed) / (ldy + 1), 128);
+                kc_max = (int)std::min<long long>((smem_budget_doubles - fixed - bottom_reserve) / (ldy + 1), 128);
                 kc_max &= ~3;                                            // whole groups of 4 columns, <= 32 groups
             }
             BigTarget bt;
@@ -400,19 +411,38 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             bt.h1 = w;
             if (bt.panel_doubles > 2048 && w >= 4) bt.h1 = ((w + 1) / 2 + 1) & ~1;   // even => both parts 16-byte aligned
             int col = 0;
-            YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
+            YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), 0, 0, (int)ymask.size()};
             ymask.resize(ymask.size() + ntI, 0u);
             int max_kc = 0;
+            struct Bottom { int row, src, col; };
+            std::vector<Bottom> bottoms;
             auto close_chunk = [&]() {
                 const int kc4 = (col - ch.col_begin + 3) & ~3;
                 for (int cc = 0; cc < col - ch.col_begin; cc++) {      // pivots of the Y columns: Dy[cc] = D[ypiv]
                     ystage_src.push_back(-1 - ypiv[ch.piv_begin + cc]);
                     ystage_dst.push_back(ldy * kc4 + cc);
                 }
+                std::stable_sort(bottoms.begin(), bottoms.end(), [](const Bottom &x, const Bottom &y) { return x.row < y.row; });
+                ch.bg_begin = (int)yb_row.size();
+                for (size_t i = 0; i < bottoms.size();) {
+                    size_t j = i;
+                    while (j < bottoms.size() && bottoms[j].row == bottoms[i].row) j++;
+                    yb_row.push_back(bottoms[i].row);
+                    for (size_t e = i; e < j; e++) {
+                        ystage_src.push_back(bottoms[e].src);
+                        ystage_dst.push_back((ldy + 1) * kc4 + (int)e);          // scalar e of the chunk, after Dy
+                        yb_col.push_back(bottoms[e].col);
+                    }
+                    yb_ptr.push_back((int)yb_col.size());
+                    i = j;
+                }
+                ch.bg_end = (int)yb_row.size();
+                bottoms.clear();
                 ch.col_end = col; ch.stage_end = (int)ystage_src.size();
                 max_kc = std::max(max_kc, ch.col_end - ch.col_begin);
                 ychunks.push_back(ch);
             };
+            int nbottom = 0;
             std::vector<std::pair<int, std::pair<int, int>>> singles;   // (local row, (panel offset, pivot column))
             for (int u = upd_ptr[t]; u < upd_ptr[t + 1]; u++) {
                 const UpdateEntry &ue = upd[u];
@@ -425,16 +455,21 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                             singles.push_back({lrow, {(int)(panel_off[ue.d] + (wd + ue.a) + (long long)k * nrowd), cd0 + k}});
                     continue;
                 }
+                int nb_col = 0;
+                for (int i = ue.a; i < nRd; i++) nb_col += rel[ue.rel + (i - ue.a)] >= w;
                 for (int k = 0; k < wd; k++) {
-                    if (col - ch.col_begin == kc_max) {   // chunk full
+                    if (col - ch.col_begin == kc_max || nbottom + nb_col > bottom_reserve) {   // chunk full
                         close_chunk();
-                        ch = YChunk{col, col, (int)ystage_src.size(), 0, (int)ypiv.size(), (int)ymask.size()};
+                        ch = YChunk{col, col, (int)ystage_src.size(), 0, (int)ypiv.size(), 0, 0, (int)ymask.size()};
                         ymask.resize(ymask.size() + ntI, 0u);
+                        nbottom = 0;
                     }
                     ypiv.push_back(cd0 + k);
                     for (int i = ue.a; i < nRd; i++) {
                         const int lrow = rel[ue.rel + (i - ue.a)], lcol = col - ch.col_begin;
-                        ystage_src.push_back((int)(panel_off[ue.d] + (wd + i) + (long long)k * nrowd));
+                        const int src = (int)(panel_off[ue.d] + (wd + i) + (long long)k * nrowd);
+                        if (lrow >= w) { bottoms.push_back(Bottom{lrow, src, lcol}); nbottom++; continue; }
+                        ystage_src.push_back(src);
                         ystage_dst.push_back(lrow + lcol * ldy);
                         ymask[ch.mask_begin + lrow / 8] |= 1u << (lcol / 4);
                     }
@@ -459,7 +494,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             big.push_back(bt);
             big_seq.push_back(t);
             max_sb_doubles = std::max(max_sb_doubles, std::max(nrow * bt.h1, bt.panel_doubles - nrow * bt.h1));
-            const long long ysize = (long long)((max_kc + 3) & ~3) * (ldy + 1);
+            const long long ysize = (long long)((max_kc + 3) & ~3) * (ldy + 1) + bottom_reserve;
             scratch_doubles = (int)std::max<long long>(scratch_doubles, fixed + std::max<long long>(ysize, aux) + 8);
         }
     }

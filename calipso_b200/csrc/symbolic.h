@@ -40,14 +40,16 @@ struct YChunk {
     int col_begin, col_end;      // Y columns of this chunk
     int stage_begin, stage_end;  // range in ystage_src / ystage_dst
     int piv_begin;               // ypiv[piv_begin + c]: pivot (permuted column) of chunk column c
+    int bg_begin, bg_end;        // bottom-row groups of this chunk (entries below the pivot rows, see yb_*)
     int mask_begin;              // ymask[mask_begin + ti]: bit g set <=> rows [8ti, 8ti+8) x columns [4g, 4g+4) of the chunk
                                  // hold a structural non-zero (the tensor-core GEMM skips the other 8x4 blocks)
 };
 struct BigTarget {
     int chunk_begin, chunk_end;
-    int ldy;                     // leading dimension of Y: rows rounded up to a multiple of 8, plus 4 (=> 8x4 fragment
+    int ldy;                     // leading dimension of Y (pivot rows only): w rounded up to a multiple of 8, plus 4 (=> 8x4 fragment
                                  // loads of the FP64 mma hit 16 distinct shared-memory banks per half-warp)
-    int ldp;                     // leading dimension of the panel work area (same rounding)
+    int ldp;                     // leading dimension of the panel work area: smallest value >= rows that is 4 mod 8 (the
+                                 // tensor-core tiles may read a few rows past the panel's last row: stores are predicated)
     int panel_doubles;           // size of the supernode's panel in the factor storage (even): one TMA bulk copy in the solves
     int asm_begin, asm_end;      // range in basm_src / basm_dst: the input entries of this supernode (fused assembly)
     int dg_begin, dg_end;        // range of diagonal-update groups (descendant columns with a single entry in this target)
@@ -123,6 +125,10 @@ struct Symbolic {
     std::vector<YChunk> ychunks;
     std::vector<int> ystage_src, ystage_dst, ypiv;
     std::vector<unsigned> ymask;
+    // entries of the staged columns BELOW the pivot rows do not enter Y (they are few: Y keeps w rows only); they are
+    // staged as scalars after Dy and applied per target row r as  S[r, 0:w] -= sum_e l_e Dy[c_e] Y[0:w, c_e]
+    std::vector<int> yb_row, yb_ptr;          // per group: local row r >= w; [groups + 1] range of entries
+    std::vector<int> yb_col;                  // per entry: column of the chunk (its scalar sits at Dy + kc4 + entry - first entry of the chunk)
     // descendant columns whose only entry in a target is one row r: they never enter Y; S[r, r] -= sum l^2 d per
     // destination group (r < w), fixed order
     std::vector<int> dg_dst, dg_ptr;          // per group: offset in the work area S; [groups + 1] range in dg_src / dg_piv
@@ -156,7 +162,7 @@ struct Symbolic {
     // still postordered (which does not change the fill) so that supernodes are contiguous.
     // Returns an empty string on success, else an error message.
     const char *analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
-                        int smem_budget_doubles = 9500);   // 76 KB: three CTAs per SM
+                        int smem_budget_doubles = 9250);   // 74 KB + 2.6 KB static + 1 KB reserved, three CTAs per SM
 };
 
 // Approximate-minimum-degree stand-in: quotient-graph minimum degree with element absorption and exact external

@@ -23,6 +23,7 @@ using namespace cb200;
     } while (0)
 
 static_assert(sizeof(cb200_options) == sizeof(Options), "cb200_options must mirror cb200::Options");
+static_assert(sizeof(Phase) == 6 * sizeof(int) && sizeof(ChainDesc) == 32, "shared-memory caches assume these layouts");
 static_assert((int)CB200_S_COUNT == (int)S_COUNT && (int)CB200_I_COUNT == (int)I_COUNT, "slot enums out of sync");
 
 // ---------------------------------------------------------------------------------------------------- batch view
@@ -70,6 +71,11 @@ struct Batch {
         if (threadIdx.x == 0) cb_chain_n = nch;                                                            \
         for (int e = threadIdx.x; e < 2 * nch; e += blockDim.x)                                            \
             cb_chain[e] = reinterpret_cast<const int4 *>(P.bdesc)[e];                                      \
+        const int nph = P.nphases <= CB_MAX_PHASES ? P.nphases : 0;                                        \
+        if (threadIdx.x == 0) cb_phase_n = nph;                                                            \
+        for (int e = threadIdx.x; e < 6 * nph; e += blockDim.x)                                            \
+            cb_phase[e] = reinterpret_cast<const int *>(P.phases)[e];                                      \
+        for (int e = threadIdx.x; e < nph + 1 && nph > 0; e += blockDim.x) cb_pphase[e] = P.pphase_ptr[e]; \
     }                                                                                                      \
     if (threadIdx.x == 0) {                                                                                \
         mbar_init(&cb_bars[0], 1);                                                                         \

@@ -196,7 +196,11 @@ __shared__ unsigned cb_bar_uses;
 __shared__ long long cb_prof[32];
 #define CB_MAX_CHAIN 64
 __shared__ int4 cb_chain[2 * CB_MAX_CHAIN];   // ChainDesc of the shared-memory supernodes (filled once per kernel)
-__shared__ int cb_chain_n;                     // number of valid entries (0: read descriptors from global memory)      // phase counters of this CTA, flushed to the instance's slots when the kernel ends
+__shared__ int cb_chain_n;
+#define CB_MAX_PHASES 48
+__shared__ int cb_phase[6 * CB_MAX_PHASES];     // the schedule (Phase records) and the bulk-pull ranges, cached per kernel
+__shared__ int cb_pphase[CB_MAX_PHASES + 1];
+__shared__ int cb_phase_n;                     // 0: read the schedule from global memory                     // number of valid entries (0: read descriptors from global memory)      // phase counters of this CTA, flushed to the instance's slots when the kernel ends
 #define CB_SCRATCH(ctx) (cb_dyn_smem)
 #define CB_RED(ctx) (cb_red)
 #else
@@ -941,7 +945,18 @@ CB_DEV void for_each_supernode(const Ctx &cta, const DevProblem &P, bool forward
     wctx.warp_scope = 1;
 #endif
     for (int pi = 0; pi < P.nphases; pi++) {
-        const Phase ph = P.phases[forward ? pi : P.nphases - 1 - pi];
+        const int pidx = forward ? pi : P.nphases - 1 - pi;
+#if CB_ON_DEVICE
+        Phase ph;
+        if (cb_phase_n > 0) {
+            const int *pp = cb_phase + 6 * pidx;
+            ph.mode = pp[0]; ph.begin = pp[1]; ph.end = pp[2]; ph.ebegin = pp[3]; ph.eend = pp[4]; ph.first_big = pp[5];
+        } else {
+            ph = P.phases[pidx];
+        }
+#else
+        const Phase ph = P.phases[pidx];
+#endif
         if (ph.mode == 2) {
             g(cta, ph.begin, ph.end, ph.ebegin, ph.eend);
         } else if (ph.mode == 1) {
@@ -1221,7 +1236,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
         },
         [&](const Ctx &, int, int, int, int) {},
         [&](int pi, int mode) {      // bulk pull: the finished phase's small supernodes -> pivot columns of chain supernodes
-            const int r0 = P.pphase_ptr[pi], r1 = P.pphase_ptr[pi + 1];
+            const int r0 = cb_phase_n > 0 ? cb_pphase[pi] : P.pphase_ptr[pi], r1 = cb_phase_n > 0 ? cb_pphase[pi + 1] : P.pphase_ptr[pi + 1];
             if (mode == 2 || r1 == r0) return;
             const int4 *__restrict__ rowi = reinterpret_cast<const int4 *>(P.prow);
             for (int r = r0 + tid; r < r1; r += nthr) {

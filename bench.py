@@ -294,7 +294,7 @@ def run_gpu(args):
     tpath2 = os.path.join(ROOT, "profiles", "lq_step_traffic.json")
     traffic = json.load(open(tpath2)).get("dram_bytes_per_launch") if os.path.exists(tpath2) else None
     tpath = os.path.join(ROOT, "profiles", "kkt_factor_solve_traffic.json")
-    kkt_traffic = json.load(open(tpath)).get("dram_bytes_per_launch") if os.path.exists(tpath) else None
+    kkt_traffic = json.load(open(tpath)).get("dram_bytes_per_instance") * B if os.path.exists(tpath) else None   # capture at batch 444, scaled
     achieved = newton_bytes / max(n_lq_launches, 1) / (ms_lq_launch * 1e-3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     kernel="k_lq_step", launches_in_timed_region=n_lq_launches, ms_per_launch=ms_lq_launch,

@@ -327,26 +327,44 @@ def run_gpu(args):
     stats_out = torch.empty((B, _lib.I_COUNT), dtype=torch.int32).pin_memory()
     h2d = sum(t.numel() * 8 for t in host_in.values())
     d2h = sum(t.numel() * 8 for t in host_out.values()) + stats_out.numel() * 4
-    lib, h, A = k.lib, k.h, _lib.A
+    lib, A = k.lib, _lib.A
+    # the batch is split over a few handles (each with its own stream) so that the H2D copies of one chunk overlap the
+    # kernels and the D2H copies of the others; every chunk does the complete upload -> hot path -> read-back
+    from calipso_b200.sharding import shard_range
+    nchunks = max(1, min(args.e2e_chunks, B))
+    bounds = [shard_range(B, c, nchunks) for c in range(nchunks)]
+    chunk_handles = [BatchKKT(Ps[0], batch=e - b, device=local) for b, e in bounds]
+
+    def at(t, b0, ctype):
+        return _lib.C.cast(t.data_ptr() + b0 * t.shape[1] * t.element_size(), ctype)
 
     def e2e_step():
-        for nm, t in host_in.items():
-            lib.cb200_set_array(h, A[nm], _lib.C.cast(t.data_ptr(), _lib.c_dp), 0, B)
-        lib.cb200_cone(h, 7, 0)
-        lib.cb200_residual(h)
-        lib.cb200_search_direction(h)
-        lib.cb200_cone_search(h)
-        for nm, t in host_out.items():
-            lib.cb200_get_array(h, A[nm], _lib.C.cast(t.data_ptr(), _lib.c_dp), 0, B)
-        lib.cb200_get_stats(h, _lib.C.cast(stats_out.data_ptr(), _lib.c_ip), 0, B)
+        for (b0, e0_), kc in zip(bounds, chunk_handles):
+            n_, hc = e0_ - b0, kc.h
+            for nm, t in host_in.items():
+                lib.cb200_set_array(hc, A[nm], at(t, b0, _lib.c_dp), 0, n_)
+            lib.cb200_cone(hc, 7, 0)
+            lib.cb200_residual(hc)
+            lib.cb200_search_direction(hc)
+            lib.cb200_cone_search(hc)
+            for nm, t in host_out.items():
+                lib.cb200_get_array_async(hc, A[nm], at(t, b0, _lib.c_dp), 0, n_)
+            lib.cb200_get_stats_async(hc, at(stats_out, b0, _lib.c_ip), 0, n_)
+        for kc in chunk_handles:
+            lib.cb200_synchronize(kc.h)
 
     for _ in range(2):
         e2e_step()
+    assert int(stats_out[:, _lib.I["status"]].abs().sum()) == 0, "e2e step reported solver errors"
     ms_e2e = timed(e2e_step, max(3, args.steps))
     e2e_value = B * world / (ms_e2e * 1e-3)
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e,
-               what="one Newton step per instance through the C ABI: H2D of evaluate!'s outputs + point, cone!, residual!, "
-                    "search_direction!, cone search, D2H of step/candidate/scalars/stats")
+               handles_per_gpu=nchunks,
+               what="one Newton step per instance through the C ABI from pinned host buffers: H2D of evaluate!'s outputs + "
+                    "point, cone!, residual!, search_direction!, cone search, D2H of step/candidate/scalars/stats; the batch "
+                    "is split over handles_per_gpu handles (one stream each) so copies overlap kernels")
+    for kc in chunk_handles:
+        kc.close()
 
     extras = {}
     if rank == 0 and world == 1 and not args.no_single:
@@ -427,6 +445,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="handles (streams) the e2e step pipelines the batch over")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

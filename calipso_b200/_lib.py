@@ -82,6 +82,8 @@ SYMBOLS = {
     "cb200_set_array": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
     "cb200_get_array": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
     "cb200_get_stats": (C.c_int, [vp, c_ip, C.c_int, C.c_int]),
+    "cb200_get_array_async": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
+    "cb200_get_stats_async": (C.c_int, [vp, c_ip, C.c_int, C.c_int]),
     "cb200_array_length": (C.c_int, [vp, C.c_int]),
     "cb200_get_profile": (C.c_int, [vp, c_llp, C.c_int]),
     "cb200_device_ptr": (vp, [vp, C.c_int]),

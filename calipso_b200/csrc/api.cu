@@ -535,6 +535,23 @@ extern "C" int cb200_get_array(cb200_handle *h, int which, double *host, int fir
     return 0;
 }
 
+extern "C" int cb200_get_array_async(cb200_handle *h, int which, double *host, int first, int count)
+{
+    if (check_array(h, which, first, count)) return -1;
+    CUDA_OK(cudaSetDevice(h->device));
+    const ArrayDesc &a = h->arr[which];
+    CUDA_OK(cudaMemcpyAsync(host, a.ptr + (long long)first * a.len, sizeof(double) * a.len * count, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+extern "C" int cb200_get_stats_async(cb200_handle *h, int *host, int first, int count)
+{
+    if (first < 0 || count < 0 || first + count > h->batch) return fail("instance range out of bounds");
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaMemcpyAsync(host, h->B.istat + (long long)first * I_COUNT, sizeof(int) * I_COUNT * count, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
 extern "C" int cb200_get_stats(cb200_handle *h, int *host, int first, int count)
 {
     if (first < 0 || count < 0 || first + count > h->batch) return fail("instance range out of bounds");

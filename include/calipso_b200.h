@@ -141,6 +141,10 @@ int cb200_get_factor(cb200_handle *h, int instance, int *Lp, int *Li, double *Lx
 int cb200_set_array(cb200_handle *h, int which, const double *host, int first_instance, int count); /* H2D, async */
 int cb200_get_array(cb200_handle *h, int which, double *host, int first_instance, int count);       /* D2H + sync */
 int cb200_get_stats(cb200_handle *h, int *host /* [count][CB200_I_COUNT] */, int first_instance, int count);
+/* the same without the final stream synchronisation (host buffers should be pinned; call cb200_synchronize before reading
+ * them): lets several handles, each on its own stream, overlap their copies with each other's kernels */
+int cb200_get_array_async(cb200_handle *h, int which, double *host, int first_instance, int count);
+int cb200_get_stats_async(cb200_handle *h, int *host, int first_instance, int count);
 int cb200_array_length(const cb200_handle *h, int which);
 /* per-instance cycle counters of the factor/solve phases, [batch][24] (thread 0 of each CTA, clock64); reset != 0
  * zeroes them afterwards.  Diagnostic only: the counters are off until this function is called for the first time

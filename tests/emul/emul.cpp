@@ -204,6 +204,10 @@ extern "C" int cb200_get_stats(cb200_handle *h, int *host, int first, int count)
     return 0;
 }
 extern "C" int cb200_get_profile(cb200_handle *, long long *, int) { return 0; }
+extern "C" int cb200_get_array(cb200_handle *h, int which, double *host, int first, int count);
+extern "C" int cb200_get_stats(cb200_handle *h, int *host, int first, int count);
+extern "C" int cb200_get_array_async(cb200_handle *h, int which, double *host, int first, int count) { return cb200_get_array(h, which, host, first, count); }
+extern "C" int cb200_get_stats_async(cb200_handle *h, int *host, int first, int count) { return cb200_get_stats(h, host, first, count); }
 extern "C" int cb200_array_length(const cb200_handle *h, int which)
 {
     if (which < 0 || which >= CB200_NUM_ARRAYS || h->len[which] == 0) return -1;

@@ -222,3 +222,84 @@ def test4(seed=0) -> DenseNLP:
         hess=lambda x: _z(3, 3), g=lambda x: _z(0), jac_g=lambda x: _z(0, 3), hess_gy=lambda x, y: _z(3, 3),
         h=lambda x: np.array([1 - x @ x]), jac_h=lambda x: (-2 * x)[None], hess_hz=lambda x, z: -2 * z[0] * np.eye(3),
         x0=rng.random(3))
+
+
+def pendulum(seed: int = 0, horizon: int = 11) -> DenseNLP:
+    """README.md:129-176 / test/examples/pendulum.jl (BASELINE cfg1): pendulum swing-up, implicit-midpoint dynamics,
+    variables [x_1, u_1, ..., x_{T-1}, u_{T-1}, x_T] (trajectory_optimization/dynamics.jl:333-340), equalities ordered
+    dynamics, then stage constraints (data.jl:51-55): n = 32, m = 24, p = 0 for T = 11.  The action guess is seeded
+    (the README draws it with randn).  Derivatives written out; second derivatives are summed where stage sparsities
+    overlap (what the reference's own Hessian test does, hessian_lagrangian.jl:296-302; SURVEY.md Appendix A.17 notes
+    that the reference's evaluate! overwrites instead -- that happens before the hot-path boundary)."""
+    T, h = horizon, 0.05
+    ml2, grav_l, damp = 0.25, 9.81 / 0.5, 0.1 / 0.25
+    nx, nu = 2, 1
+    n = T * nx + (T - 1) * nu
+    m = (T - 1) * nx + 2 * nx
+    ix = [t * (nx + nu) for t in range(T)]                 # offset of x_t
+    iu = [t * (nx + nu) + nx for t in range(T - 1)]        # offset of u_t
+    x_init, x_goal = np.array([0.0, 0.0]), np.array([np.pi, 0.0])
+
+    def f(v):
+        c = 0.0
+        for t in range(T):
+            c += 0.1 * v[ix[t]:ix[t] + 2] @ v[ix[t]:ix[t] + 2]
+        for t in range(T - 1):
+            c += 0.1 * v[iu[t]] ** 2
+        return c
+
+    def grad(v):
+        return 0.2 * v
+
+    def hess(v):
+        return 0.2 * np.eye(n)
+
+    def g(v):
+        out = np.zeros(m)
+        for t in range(T - 1):
+            x, y, u = v[ix[t]:ix[t] + 2], v[ix[t + 1]:ix[t + 1] + 2], v[iu[t]]
+            xm = 0.5 * (x + y)
+            fc = np.array([xm[1], u / ml2 - grav_l * np.sin(xm[0]) - damp * xm[1]])
+            out[2 * t:2 * t + 2] = y - (x + h * fc)
+        out[2 * (T - 1):2 * (T - 1) + 2] = v[ix[0]:ix[0] + 2] - x_init
+        out[2 * (T - 1) + 2:] = v[ix[T - 1]:ix[T - 1] + 2] - x_goal
+        return out
+
+    def jac_g(v):
+        J = np.zeros((m, n))
+        for t in range(T - 1):
+            x, y = v[ix[t]:ix[t] + 2], v[ix[t + 1]:ix[t + 1] + 2]
+            c = np.cos(0.5 * (x[0] + y[0]))
+            r = 2 * t
+            # d1 = y1 - x1 - h * 0.5 (x2 + y2)
+            J[r, ix[t]] = -1.0; J[r, ix[t] + 1] = -0.5 * h
+            J[r, ix[t + 1]] = 1.0; J[r, ix[t + 1] + 1] = -0.5 * h
+            # d2 = y2 - x2 - h (u / ml2 - grav_l sin(xm1) - damp xm2)
+            J[r + 1, ix[t]] = 0.5 * h * grav_l * c; J[r + 1, ix[t + 1]] = 0.5 * h * grav_l * c
+            J[r + 1, ix[t] + 1] = -1.0 + 0.5 * h * damp; J[r + 1, ix[t + 1] + 1] = 1.0 + 0.5 * h * damp
+            J[r + 1, iu[t]] = -h / ml2
+        r = 2 * (T - 1)
+        J[r, ix[0]] = 1.0; J[r + 1, ix[0] + 1] = 1.0
+        J[r + 2, ix[T - 1]] = 1.0; J[r + 3, ix[T - 1] + 1] = 1.0
+        return J
+
+    def hess_gy(v, y_):
+        H = np.zeros((n, n))
+        for t in range(T - 1):
+            x, y = v[ix[t]:ix[t] + 2], v[ix[t + 1]:ix[t + 1] + 2]
+            d2 = -0.25 * h * grav_l * np.sin(0.5 * (x[0] + y[0])) * y_[2 * t + 1]     # d^2 d2 / d(x1|y1)^2
+            for a in (ix[t], ix[t + 1]):
+                for b in (ix[t], ix[t + 1]):
+                    H[a, b] += d2
+        return H
+
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros(n)
+    for t in range(T):
+        x0[ix[t]:ix[t] + 2] = x_init + (x_goal - x_init) * t / (T - 1)       # linear_interpolation, utilities.jl:10
+    for t in range(T - 1):
+        x0[iu[t]] = rng.standard_normal()
+    P = DenseNLP("pendulum", n, m, 0, 0, np.zeros(0, dtype=np.int32), f, grad, hess, g, jac_g, hess_gy,
+                 lambda v: np.zeros(0), lambda v: np.zeros((0, n)), lambda v, z: np.zeros((n, n)), x0)
+    P.x_goal, P.ix = x_goal, ix
+    return P

@@ -90,6 +90,17 @@ def test_portfolio():
     assert np.abs(P.b - P.A @ o.solution[:P.n] - s).max() < 1e-4
 
 
+def test_pendulum_readme_quickstart():
+    """README.md:129-176 / test/examples/pendulum.jl:64-73 (BASELINE cfg1): converges, dynamics feasible, goal reached."""
+    P = problems.pendulum()
+    o, rc = solve(P)
+    assert rc == 1
+    check_criteria(o)
+    x = o.solution[:P.n]
+    assert np.abs(P.g(x)).max() < 1e-4
+    assert np.abs(x[P.ix[-1]:P.ix[-1] + 2] - P.x_goal).max() < 1e-4
+
+
 def test_lqc_family_converges_and_is_feasible():
     for P in (lqc.tiny(), lqc.cfg2()):
         o = orc.from_problem(P)

@@ -63,6 +63,7 @@ struct Batch {
 };
 
 #define CB_THREADS 256
+#define CB_THREADS_WIDE 512
 #define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
 #define CTX_SETUP                                                                                          \
     if (threadIdx.x < 32) cb_prof[threadIdx.x] = 0;                                                        \
@@ -111,7 +112,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_residual(const __gr
     if (ctx.tid == 0) I.scal[S_THETA] = th;
 }
 
-__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_search_direction(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_search_direction(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
 {
     KERNEL_PROLOGUE
     int st = search_direction(ctx, P, I, o);
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_begin(const __gr
     solve_begin_lq(ctx, P, I, o, warmstart);
 }
 
-__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
 {
     KERNEL_PROLOGUE
     solve_step_lq(ctx, P, I, o);
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_step(const __gri
 
 // LinearSolver seam: factor the generic matrix / solve in place.  These two are the "KKT LDL^T solve" whose HBM
 // roofline bench.py reports (B_unit).
-__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_factor(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int assemble_generic)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_ldl_factor(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int assemble_generic)
 {
     CTX_SETUP
     const int b = blockIdx.x;
@@ -188,7 +192,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_factor(const __
     PROF_FLUSH(B.prof ? B.prof + b * (long long)PROF_COUNT : nullptr);
 }
 
-__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {
     CTX_SETUP
     const int b = blockIdx.x;
@@ -201,7 +206,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_ldl_solve(const __g
 }
 
 // KKT path: assemble + factor with the current regularisation (no inertia loop) -- used by the roofline bench
-__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nsolves)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_kkt_factor_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nsolves)
 {
     KERNEL_PROLOGUE
     ProfTimer pt{I.prof, 0};
@@ -214,7 +220,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_kkt_factor_solve(co
 }
 
 // differentiate!: one factorisation, num_parameters reduced solves with recovery, sign flip (differentiate.jl:13-57)
-__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_differentiate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nparam,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_differentiate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nparam,
                                                                          const double *H, double *S)
 {
     KERNEL_PROLOGUE
@@ -279,6 +286,7 @@ struct cb200_handle {
     void *comm = nullptr;
     int nranks = 1;
     int nnzW = 0, nnzG = 0, nnzC = 0;
+    bool wide = false;          // heavy kernels with CB_THREADS_WIDE threads per instance (small batches)
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
 };
 
@@ -353,6 +361,12 @@ static bool finish_batch(cb200_handle *h)
     h->allocs.push_back(d);
     h->prof_store = (long long *)d;   // counters stay off (B.prof == nullptr) until cb200_get_profile is first called
     h->B.prof = nullptr;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        h->wide = h->batch <= sms;
+        if (const char *e = getenv("CB200_THREADS")) h->wide = atoi(e) > CB_THREADS;   // testing / tuning override
+    }
     h->B.scratch_doubles = h->sym().scratch_doubles;
     h->smem_bytes = (size_t)h->B.scratch_doubles * sizeof(double);
     return true;
@@ -607,15 +621,22 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
         CUDA_OK(cudaGetLastError());                                          \
     } while (0)
 // kernels that factor or solve get the CTA work area (panel + Y staging) as dynamic shared memory
+#define LAUNCH_SMEM_T(kernel, T, ...)                                                                     \
+    do {                                                                                                  \
+        static size_t configured = 0;                                                                     \
+        if (h->smem_bytes > configured) {                                                                 \
+            CUDA_OK(cudaFuncSetAttribute(kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
+            configured = h->smem_bytes;                                                                   \
+        }                                                                                                 \
+        kernel<T><<<h->batch, T, h->smem_bytes, h->stream>>>(__VA_ARGS__);                                \
+    } while (0)
+// Small batches (at most one CTA per SM anyway) run the heavy kernels with CB_THREADS_WIDE threads per instance: the
+// parallel phases (gathers, tensor-core tiles, bulk solve passes, J v) get twice the warps, the register cap doubles.
 #define LAUNCH_SMEM(kernel, ...)                                                                          \
     do {                                                                                                  \
         CUDA_OK(cudaSetDevice(h->device));                                                                \
-        static size_t configured_##kernel = 0;                                                            \
-        if (h->smem_bytes > configured_##kernel) {                                                        \
-            CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
-            configured_##kernel = h->smem_bytes;                                                          \
-        }                                                                                                 \
-        kernel<<<h->batch, CB_THREADS, h->smem_bytes, h->stream>>>(__VA_ARGS__);                          \
+        if (h->wide) LAUNCH_SMEM_T(kernel, CB_THREADS_WIDE, __VA_ARGS__);                                 \
+        else LAUNCH_SMEM_T(kernel, CB_THREADS, __VA_ARGS__);                                              \
         CUDA_OK(cudaGetLastError());                                                                      \
     } while (0)
 #define NEED_KKT() if (h->generic) return fail("not available on a LinearSolver-seam handle")
@@ -657,12 +678,13 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
     int rc = 0;
     do {
         if (cudaMemcpyAsync(dH, H_host, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = fail("H2D failed"); break; }
-        static size_t configured = 0;
-        if (h->smem_bytes > configured) {
-            if (cudaFuncSetAttribute(k_differentiate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
-            configured = h->smem_bytes;
+        if (h->wide) {
+            if (cudaFuncSetAttribute(k_differentiate<CB_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            k_differentiate<CB_THREADS_WIDE><<<h->batch, CB_THREADS_WIDE, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS);
+        } else {
+            if (cudaFuncSetAttribute(k_differentiate<CB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            k_differentiate<CB_THREADS><<<h->batch, CB_THREADS, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS);
         }
-        k_differentiate<<<h->batch, CB_THREADS, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS);
         if (cudaGetLastError() != cudaSuccess) { rc = fail("k_differentiate launch failed"); break; }
         if (cudaMemcpyAsync(S_host, dS, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = fail("D2H failed"); break; }
         cudaError_t e = cudaStreamSynchronize(h->stream);

@@ -183,7 +183,19 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
+        saved_stdout0 = os.dup(1)                       # ... and whatever the communicator set-up still prints
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t0 = torch.zeros(1, device="cuda")
+            dist.all_reduce(t0)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout0, 1)
+            os.close(saved_stdout0)
     B = args.batch
     distinct = min(B, args.distinct)
     # instances: `distinct` different seeds per rank, tiled over the batch (values differ per seed, pattern shared)
@@ -194,9 +206,20 @@ def run_gpu(args):
     k.load_lq(plist)
     X0 = np.stack([P.x0 for P in plist])
     if world > 1:
-        uid = [k.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        k.comm_init(rank, world, uid[0])
+        saved_stdout = os.dup(1)                        # anything NCCL prints while initialising goes to stderr
+        os.dup2(2, 1)
+        try:
+            uid = [k.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            k.comm_init(rank, world, uid[0])
+            k.allreduce_counts()                        # first collective (lazy communicator setup) inside the redirect
+            t0 = torch.zeros(1, device="cuda")
+            dist.all_reduce(t0)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     stream = torch.cuda.ExternalStream(k.lib.cb200_stream(k.h), device=torch.device("cuda", local))
 
     def barrier():

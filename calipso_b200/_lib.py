@@ -87,6 +87,7 @@ SYMBOLS = {
     "cb200_array_length": (C.c_int, [vp, C.c_int]),
     "cb200_get_profile": (C.c_int, [vp, c_llp, C.c_int]),
     "cb200_device_ptr": (vp, [vp, C.c_int]),
+    "cb200_values_changed": (C.c_int, [vp]),
     "cb200_stream": (vp, [vp]),
     "cb200_synchronize": (C.c_int, [vp]),
     "cb200_set_options": (C.c_int, [vp, C.POINTER(COptions)]),

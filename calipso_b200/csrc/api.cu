@@ -599,6 +599,7 @@ extern "C" void *cb200_device_ptr(cb200_handle *h, int which)
     if (which < 0 || which >= CB200_NUM_ARRAYS) return nullptr;
     return h->arr[which].ptr;
 }
+extern "C" int cb200_values_changed(cb200_handle *h) { h->values_dirty = true; return 0; }
 extern "C" void *cb200_stream(cb200_handle *h) { return (void *)h->stream; }
 extern "C" int cb200_synchronize(cb200_handle *h)
 {

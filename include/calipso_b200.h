@@ -151,6 +151,9 @@ int cb200_array_length(const cb200_handle *h, int which);
  * (that call returns zeros) because they cost a global read-modify-write per phase. */
 int cb200_get_profile(cb200_handle *h, long long *host, int reset);
 void *cb200_device_ptr(cb200_handle *h, int which);   /* base of the instance-major device array */
+/* The library keeps row-ordered copies of the W and G values (refreshed lazily after cb200_set_array).  A caller that
+ * writes CB200_W_VALUES / CB200_G_VALUES through cb200_device_ptr must announce it with this call. */
+int cb200_values_changed(cb200_handle *h);
 void *cb200_stream(cb200_handle *h);                  /* cudaStream_t of the handle */
 int cb200_synchronize(cb200_handle *h);
 int cb200_set_options(cb200_handle *h, const cb200_options *options);

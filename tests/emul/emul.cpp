@@ -214,6 +214,7 @@ extern "C" int cb200_array_length(const cb200_handle *h, int which)
     return (int)h->len[which];
 }
 extern "C" void *cb200_device_ptr(cb200_handle *h, int which) { return h->arr[which].data(); }
+extern "C" int cb200_values_changed(cb200_handle *) { return 0; }
 extern "C" void *cb200_stream(cb200_handle *) { return nullptr; }
 extern "C" int cb200_synchronize(cb200_handle *) { return 0; }
 extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)

@@ -1020,15 +1020,15 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
                 const int4 *__restrict__ e4 = reinterpret_cast<const int4 *>(P.leaf_e4) + ebegin;
                 int e = ctx.tid;
                 const int st = ctx.nthr;
-                for (; e + 3 * st < cnt; e += 4 * st) {
-                    int4 d[4];
-                    double v[4];
+                for (; e + 7 * st < cnt; e += 8 * st) {      // eight entries in flight per thread
+                    int4 d[8];
+                    double v[8];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) d[u] = e4[e + u * st];
+                    for (int u = 0; u < 8; u++) d[u] = e4[e + u * st];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = ksrc_load(K, d[u].w) * Dinv[d[u].y];
+                    for (int u = 0; u < 8; u++) v[u] = ksrc_load(K, d[u].w) * Dinv[d[u].y];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { pan[d[u].x] = v[u]; Lcsr[d[u].z] = v[u]; }
+                    for (int u = 0; u < 8; u++) { pan[d[u].x] = v[u]; Lcsr[d[u].z] = v[u]; }
                 }
                 for (; e < cnt; e += st) {
                     const int4 d = e4[e];

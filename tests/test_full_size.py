@@ -99,3 +99,41 @@ def test_cfg3_batch_solve_meets_stopping_criteria():
         assert np.abs(P.G() @ x + P.g0).max() <= 1e-4
         h = P.C() @ x + P.h0
         assert h[:P.num_nonnegative].min() >= -1e-4
+
+
+def test_narrow_and_wide_kernel_instantiations_agree():
+    """Batches of at most one CTA per SM run the 512-thread instantiations of the heavy kernels, larger batches the
+    256-thread ones (three CTAs per SM).  Same instances through both: same iteration counts, same solutions."""
+    Ps = [lqc.tiny(i) for i in range(4)]
+    big = 200                                   # > 148 SMs => narrow kernels
+    k = BatchKKT(Ps[0], batch=big, binding=backends.binding("cuda"))
+    k.load_lq([Ps[i % 4] for i in range(big)])
+    k.initialize(np.stack([Ps[i % 4].x0 for i in range(big)]))
+    k.lq_begin()
+    r = k.lq_solve(max_steps=300, check_every=3)
+    assert r["converged"] == big
+    W, it = k.get("POINT"), k.stats()["total_iterations"]
+    k1 = BatchKKT(Ps[0], batch=4, binding=backends.binding("cuda"))          # wide kernels
+    k1.load_lq(Ps)
+    k1.initialize(np.stack([P.x0 for P in Ps]))
+    k1.lq_begin()
+    assert k1.lq_solve(max_steps=300, check_every=3)["converged"] == 4
+    W1, it1 = k1.get("POINT"), k1.stats()["total_iterations"]
+    for i in range(big):
+        assert it[i] == it1[i % 4]
+        assert np.abs(W[i] - W1[i % 4]).max() <= 1e-9 * max(1.0, np.abs(W1[i % 4]).max())
+    # and a cfg3-sized KKT solve unit through the narrow path: direction solves the full Newton system
+    Pc = [lqc.cfg3(i) for i in range(2)]
+    kc = BatchKKT(Pc[0], batch=150, binding=backends.binding("cuda"))
+    kc.load_lq([Pc[i % 2] for i in range(150)])
+    kc.initialize(np.stack([Pc[i % 2].x0 for i in range(150)]))
+    kc.lq_begin()
+    kc.lq_step(2)
+    kc.lq_evaluate(2 | 16 | 32)
+    kc.cone(barrier=True, barrier_gradient=True, product=True)
+    kc.residual()
+    kc.search_direction()
+    st = kc.stats()
+    assert np.all(st["status"] == 0) and np.all(st["inertia_pos"] == Pc[0].n)
+    e = kc.get("RESIDUAL") - kc.jacobian_times(kc.get("STEP"))
+    assert np.abs(e).max() <= 1e-10

@@ -730,13 +730,20 @@ extern "C" int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, l
     if (check_every <= 0) check_every = 1;
     int done = 0;
     long long c[4] = {h->batch, 0, 0, 0};
+    const bool wide0 = h->wide;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     while (done < max_steps) {
         int chunk = std::min(check_every, max_steps - done);
-        if (cb200_lq_step(h, chunk)) return -1;
+        if (cb200_lq_step(h, chunk)) { h->wide = wide0; return -1; }
         done += chunk;
-        if (cb200_allreduce_counts(h, c)) return -1;
+        if (cb200_allreduce_counts(h, c)) { h->wide = wide0; return -1; }
         if (c[0] == 0) break;
+        // the tail of a batched solve: once the instances still running (converged ones exit at once) fit one CTA per
+        // SM, the 512-thread instantiations finish their iterations sooner
+        if (!getenv("CB200_THREADS") && c[0] <= (long long)sms * h->nranks) h->wide = true;
     }
+    h->wide = wide0;
     if (counts) for (int k = 0; k < 4; k++) counts[k] = c[k];
     if (steps_done) *steps_done = done;
     return 0;

@@ -455,7 +455,6 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     bool ok = true;
     fill_symbolic(P, h->gsym, [&](const auto &v) { return upload(h, v, ok); });
     P.nnzA = Ap[N];
-    P.dA = upload(h, h->gsym.dest, ok);
     Batch &B = h->B;
     B.count = batch;
     B.panels = dalloc(h, P.panel_total, ok); B.D = dalloc(h, N, ok); B.Dinv = dalloc(h, N, ok);

@@ -45,7 +45,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     int n, m, p, N, total;
     int q_nn, nsoc, tri_total;
     int nnzW, nnzG, nnzC, nnzWf;               // nnzWf: entries of the symmetric W by rows (both triangles)
-    const int *soc_off, *soc_dims, *soc_tri;  // soc_tri[k]: offset of cone k's upper-triangle entries in dZsoc
+    const int *soc_off, *soc_dims, *soc_tri;  // soc_tri[k]: offset of cone k's upper-triangle entries in the kx block
     // patterns
     const int *Wp, *Wi, *Wdiag;               // upper triangle CSC, Wdiag[j] = position of (j,j)
     Csr Wfull;                                 // symmetric W by rows (both triangles), src -> position in W values
@@ -90,9 +90,6 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     int max_big_nR;
     const int *parts_fwd, *parts_bwd;          // (panel offset, doubles) of the TMA copies of the solves, in issue order
     int nparts_fwd, nparts_bwd;
-    // assembly destinations (offsets into the panel storage)
-    const long long *dW, *dG, *dC, *dY, *dZnn, *dZsoc;
-    const long long *dA;                       // generic-matrix mode (LinearSolver seam): one per input entry
     int nnzA;
 };
 

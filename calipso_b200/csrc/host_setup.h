@@ -16,7 +16,6 @@ struct HostProblem {
     int n = 0, m = 0, p = 0, N = 0, total = 0, q_nn = 0, nsoc = 0, tri_total = 0, nnzW = 0, nnzG = 0, nnzC = 0;
     std::vector<int> soc_off, soc_d, soc_tri, Wp, Wi, Wdiag, Wfp, Wfc, Wfs, Gp, Gi, Cp, Ci, Grp, Gcj, Gsrc, Crp, Ccj,
         Csrc, Kp, Ki;
-    std::vector<long long> dW, dG, dC, dY, dZnn, dZsoc;
     Symbolic sym;
 
     static void csr_view(int nrows, int ncols, const int *cp, const int *ri, std::vector<int> &rp, std::vector<int> &cj,
@@ -111,12 +110,6 @@ struct HostProblem {
         Kp[N] = (int)Ki.size();
         const char *msg = sym.analyze(N, Kp.data(), Ki.data(), perm, big_threshold);
         if (msg[0]) return msg;
-        auto gather = [&](const std::vector<int> &e) {
-            std::vector<long long> d(e.size());
-            for (size_t k = 0; k < e.size(); k++) d[k] = sym.dest[e[k]];
-            return d;
-        };
-        dW = gather(eW); dG = gather(eG); dC = gather(eC); dY = gather(eY); dZnn = gather(eZnn); dZsoc = gather(eZsoc);
         // value codes of the fused assembly: array id << 30 | offset with arrays 0 = W values, 1 = G values,
         // 2 = C values, 3 = computed entries kx = [W diagonal + eps_p (n) | y diagonal (m) | nonnegative z diagonal (q_nn) |
         // second-order z blocks (tri_total)]
@@ -204,8 +197,7 @@ template <class Up> void fill_problem(DevProblem &P, const HostProblem &H, Up up
     P.Gp = up(H.Gp); P.Gi = up(H.Gi); P.Cp = up(H.Cp); P.Ci = up(H.Ci);
     P.Grow = Csr{up(H.Grp), up(H.Gcj), up(H.Gsrc)};
     P.Crow = Csr{up(H.Crp), up(H.Ccj), up(H.Csrc)};
-    P.dW = up(H.dW); P.dG = up(H.dG); P.dC = up(H.dC); P.dY = up(H.dY); P.dZnn = up(H.dZnn); P.dZsoc = up(H.dZsoc);
-    P.dA = nullptr; P.nnzA = 0;
+    P.nnzA = 0;
 }
 
 }  // namespace cb200

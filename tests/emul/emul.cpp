@@ -136,7 +136,6 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     if (msg[0]) { fail(msg); delete h; return nullptr; }
     fill_symbolic(h->P, h->gsym, [](const auto &v) { return v.data(); });
     h->P.nnzA = Ap[N];
-    h->P.dA = h->gsym.dest.data();
     h->arr.resize(X_COUNT);
     h->len.assign(X_COUNT, 0);
     for (int w : {(int)CB200_PIVOTS, (int)X_DINV, (int)X_XP, (int)CB200_RHS}) alloc(h, w, N);

@@ -50,3 +50,27 @@ def test_no_cpu_fallback_without_a_device():
     import pytest
     with pytest.raises(Exception, match="no CUDA device"):
         BatchKKT(lqc.tiny(), binding=b)
+
+
+def test_async_readback_equals_blocking_readback():
+    """cb200_get_array_async / cb200_get_stats_async + cb200_synchronize return what the blocking calls return
+    (emulation backend here; the GPU path is exercised by bench.py's pipelined e2e step)."""
+    import numpy as np
+    from calipso_b200 import lqc
+    from calipso_b200.solver import BatchKKT
+    b = backends.binding("emul")
+    P = lqc.tiny()
+    k = BatchKKT(P, batch=2, binding=b)
+    k.load_lq([P, lqc.tiny(1)])
+    k.initialize(np.stack([P.x0, lqc.tiny(1).x0]))
+    k.lq_begin()
+    k.lq_step(2)
+    ref = k.get("POINT")
+    out = np.zeros_like(ref)
+    assert b.lib.cb200_get_array_async(k.h, _lib.A["POINT"], _lib.dp(out), 0, 2) == 0
+    st = np.zeros((2, _lib.I_COUNT), dtype=np.int32)
+    assert b.lib.cb200_get_stats_async(k.h, _lib.ip(st), 0, 2) == 0
+    assert b.lib.cb200_synchronize(k.h) == 0
+    assert np.array_equal(out, ref)
+    assert np.array_equal(st[:, _lib.I["total_iterations"]], k.stats()["total_iterations"])
+    assert b.lib.cb200_values_changed(k.h) == 0

@@ -307,6 +307,8 @@ def run_gpu(args):
     for _ in range(3):
         k.kkt_factor_solve(1)
     ms_kkt = timed(lambda: k.kkt_factor_solve(1), 10)
+    ms_fact = timed(lambda: k.kkt_factor_solve(0), 10)                 # assemble + factor only
+    ms_solve = (timed(lambda: k.kkt_factor_solve(5), 5) - ms_fact) / 5  # one reduced solve (+ rhs / recovery)
     b_unit = 12 * info["nnzK"] + 36 * info["nnzL"] + 40 * info["N"]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -330,6 +332,14 @@ def run_gpu(args):
                     kkt_solve=dict(kernel="k_kkt_factor_solve", achieved=kkt_achieved, frac=kkt_achieved / peak,
                                    algorithmic_bytes_per_kkt_solve=b_unit, kkt_solves_per_launch=B, ms_per_launch=ms_kkt,
                                    kkt_solve_ms_per_instance_batched=ms_kkt / B, traffic=kkt_traffic,
+                                   factor=dict(ms_per_launch=ms_fact, algorithmic_bytes=b_asm + b_factor,
+                                               achieved=(b_asm + b_factor) * B / (ms_fact * 1e-3) / 1e9,
+                                               frac=(b_asm + b_factor) * B / (ms_fact * 1e-3) / 1e9 / peak),
+                                   reduced_solve=dict(ms_per_launch=ms_solve, algorithmic_bytes=b_solve,
+                                                      achieved=b_solve * B / (ms_solve * 1e-3) / 1e9,
+                                                      frac=b_solve * B / (ms_solve * 1e-3) / 1e9 / peak,
+                                                      what="L, D, L' sweeps of the reduced system incl. reduced rhs and "
+                                                           "recovery: B_solve = 24 nnz(L) + 24 N"),
                                    what="assemble + LDL' factor + 1 reduced solve with recovery per instance: the 'KKT solve' "
                                         "unit of SURVEY 8(d), B_unit = 12 nnz(K) + 36 nnz(L) + 40 N"))
     # ---- e2e: the reference-facing hot path through the C ABI with HOST buffers (pinned), copies inside the timing

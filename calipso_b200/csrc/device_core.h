@@ -1090,9 +1090,10 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     unsigned issued = cb_bar_uses, consumed = issued;
     const int *parts = P.parts_fwd;
     int nparts = P.nparts_fwd, next_part = 0;
-    auto issue = [&]() {    // called by all threads after a CTA barrier that freed the slot; thread 0 launches the copy
+    auto issue = [&]() {    // called by all threads after a CTA barrier that freed the slot; the first lane of the LAST warp
+                            // launches the copy (warp 0 runs the triangular sweeps: keep the proxy fence off its path)
         if (next_part < nparts) {
-            if (tid == 0) {
+            if (tid == nthr - 32) {
                 const int off = parts[2 * next_part];
                 const unsigned bytes = (unsigned)parts[2 * next_part + 1] * 8u;
                 const int slot = issued & 1;
@@ -1111,6 +1112,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
         return slot;
     };
     __syncthreads();
+    ps.stop(PROF_SF_PULL);                                        // (counter: permutation gather)
     issue();
     // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final);
     // four lanes per column, columns without leaf descendants are not visited
@@ -1233,6 +1235,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
         },
         [&](const Ctx &, int, int, int, int) {},
         [&](int pi, int mode) {      // bulk pull: the finished phase's small supernodes -> pivot columns of chain supernodes
+            ps.stop(mode == 1 ? PROF_SF_SWEEP : PROF_SF_OTHER);      // (counters: chain supernodes / small supernodes)
             const int r0 = cb_phase_n > 0 ? cb_pphase[pi] : P.pphase_ptr[pi], r1 = cb_phase_n > 0 ? cb_pphase[pi + 1] : P.pphase_ptr[pi + 1];
             if (mode == 2 || r1 == r0) return;
             const int4 *__restrict__ rowi = reinterpret_cast<const int4 *>(P.prow);
@@ -1251,6 +1254,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
+    ps.stop(PROF_SF_PUSH);                                        // (counter: D^-1 scaling and bulk pulls after the last phase)
     parts = P.parts_bwd;
     nparts = P.nparts_bwd;
     next_part = 0;
@@ -1344,7 +1348,6 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             ctx.sync();
         },
         [&](const Ctx &c, int begin, int end, int, int) {   // singleton leaves: four lanes per leaf
-            ps.stop(PROF_SB_OTHER);
             const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.leaf_info) + begin;
             const int *__restrict__ rows = P.rows;
             const int sub = tid & 3, grp = tid >> 2, ngrp = nthr >> 2, cnt = end - begin;
@@ -1378,13 +1381,15 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             (void)c;
             __syncthreads();
             ps.stop(PROF_SB_LEAVES);
-        });
+        },
+        [&](int, int mode) { if (mode != 2) ps.stop(mode == 1 ? PROF_SB_SWEEP : PROF_SB_GATHER); });   // (counters: chain / small)
     for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
     if (tid == 0 && istat) istat[I_SOLVES]++;
     __syncthreads();
     if (tid == 0) cb_bar_uses = issued;
     __syncthreads();
     pt.stop(PROF_SOLVE_BWD);
+    ps.stop(PROF_SB_OTHER);                                       // (counter: permutation scatter)
 }
 #endif
 

@@ -564,7 +564,7 @@ CB_DEV void factor_supernode(const Ctx &ctx, const DevProblem &P, double *pan, d
 }
 
 #if CB_ON_DEVICE
-// ---- asynchronous copies: TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier, and cp.async (SASS LDGSTS)
+// ---- asynchronous copies: TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 {
@@ -588,14 +588,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 #endif
 
 #if CB_ON_DEVICE

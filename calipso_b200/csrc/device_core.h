@@ -1193,12 +1193,21 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                         const int part = tid & 3;
                         for (int base = 0; base < nR; base += nthr >> 2) {
                             const int i = base + (tid >> 2);
-                            double acc = 0.0;
+                            double a0 = 0.0, a1 = 0.0;      // two accumulators per thread
                             if (i < nR) {
-                                const double *Lr = L + w + i;
-#pragma unroll 4
-                                for (int k = k0 + part; k < k1; k += 4) acc += Lr[k * nrow] * yv[k];
+                                const double *Lr = L + w + i + (k0 + part) * nrow;
+                                const double *yp = yv + k0 + part;
+                                const int cnt = (k1 - k0 - part + 3) >> 2;
+                                int j = 0;
+                                for (; j + 1 < cnt; j += 2) {
+                                    a0 += Lr[0] * yp[0];
+                                    a1 += Lr[4 * nrow] * yp[4];
+                                    Lr += 8 * nrow;
+                                    yp += 8;
+                                }
+                                if (j < cnt) a0 += Lr[0] * yp[0];
                             }
+                            double acc = a0 + a1;
                             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                             if (part == 0 && i < nR) xs[base == 0 ? rI : R[i]] -= acc;
@@ -1281,12 +1290,18 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                         const int part = tid & 3;
                         for (int base = k0; base < k1; base += nthr >> 2) {
                             const int k = base + (tid >> 2);
-                            double acc = 0.0;
+                            double a0 = 0.0, a1 = 0.0;
                             if (k < k1) {
                                 const double *Lc = L + k * nrow;
-#pragma unroll 4
-                                for (int r = k1 + part; r < nrow; r += 4) acc += Lc[r] * (r < w ? xs[c0 + r] : xr[r - w]);
+                                const double *xp = xs + c0;
+                                int r = k1 + part;
+                                for (; r + 4 < w; r += 8) { a0 += Lc[r] * xp[r]; a1 += Lc[r + 4] * xp[r + 4]; }   // pivots solved before
+                                if (r < w) { a0 += Lc[r] * xp[r]; r += 4; }
+                                const double *xq = xr - w;                                                     // rows R
+                                for (; r + 4 < nrow; r += 8) { a0 += Lc[r] * xq[r]; a1 += Lc[r + 4] * xq[r + 4]; }
+                                if (r < nrow) a0 += Lc[r] * xq[r];
                             }
+                            double acc = a0 + a1;
                             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                             if (part == 0 && k < k1) yv[k] = acc;

@@ -99,6 +99,9 @@ SYMBOLS = {
     "cb200_kkt_factor_solve": (C.c_int, [vp, C.c_int]),
     "cb200_jacobian_times": (C.c_int, [vp, c_dp, c_dp]),
     "cb200_differentiate": (C.c_int, [vp, C.c_int, c_dp, c_dp]),
+    "cb200_scatter_plan": (C.c_int, [vp, C.c_int, C.c_int, c_ip, c_ip, c_ip]),
+    "cb200_scatter": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
+    "cb200_scatter_buffer": (vp, [vp, C.c_int]),
     "cb200_lq_evaluate": (C.c_int, [vp, C.c_int, C.c_int]),
     "cb200_lq_begin": (C.c_int, [vp, C.c_int]),
     "cb200_lq_step": (C.c_int, [vp, C.c_int]),

@@ -237,6 +237,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS :
     PROF_FLUSH(I.prof);
 }
 
+// evaluate!'s cache scatter: grid = (chunks of the pattern, instances); coalesced index reads and value
+// writes, gathered cache reads
+__global__ void __launch_bounds__(256) k_scatter(int nnz, int ncaches, const int *__restrict__ idx,
+                                                 const double *__restrict__ caches, long long cache_total,
+                                                 double *__restrict__ out, long long out_len, int first_instance)
+{
+    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, nullptr, nullptr, nullptr, nullptr};
+    const long long b = first_instance + blockIdx.y;
+    scatter_caches(ctx, nnz, ncaches, idx, caches + b * cache_total, out + b * out_len, blockIdx.x * blockDim.x,
+                   gridDim.x * blockDim.x);
+}
+
 __global__ void k_count_states(Batch B, long long *counts)
 {
     __shared__ int c[4];
@@ -287,6 +299,7 @@ struct cb200_handle {
     int nranks = 1;
     int nnzW = 0, nnzG = 0, nnzC = 0;
     bool wide = false;          // heavy kernels with CB_THREADS_WIDE threads per instance (small batches)
+    struct Scatter { ScatterPlan plan; const int *d_idx = nullptr; double *d_caches = nullptr; } scatter[3];   // W, G, C
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
 };
 
@@ -693,6 +706,63 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
     cudaFree(dH);
     cudaFree(dS);
     return rc;
+}
+
+static int scatter_slot(int which)
+{
+    return which == CB200_W_VALUES ? 0 : which == CB200_G_VALUES ? 1 : which == CB200_C_VALUES ? 2 : -1;
+}
+
+extern "C" int cb200_scatter_plan(cb200_handle *h, int which, int ncaches, const int *cache_len, const int *rows, const int *cols)
+{
+    NEED_KKT();
+    const int slot = scatter_slot(which);
+    if (slot < 0) return fail("cb200_scatter_plan: which must be CB200_W_VALUES, CB200_G_VALUES or CB200_C_VALUES");
+    if (slot > 0 && ncaches != 1) return fail("cb200_scatter_plan: the G and C values have one cache each");
+    const HostProblem &H = h->hp;
+    cb200_handle::Scatter &sc = h->scatter[slot];
+    std::string err = slot == 0 ? sc.plan.build(H.n, H.n, H.Wp.data(), H.Wi.data(), true, ncaches, cache_len, rows, cols)
+                    : slot == 1 ? sc.plan.build(H.m, H.n, H.Gp.data(), H.Gi.data(), false, ncaches, cache_len, rows, cols)
+                                : sc.plan.build(H.p, H.n, H.Cp.data(), H.Ci.data(), false, ncaches, cache_len, rows, cols);
+    if (!err.empty()) { sc.plan = ScatterPlan(); return fail(err); }
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));      // a previous plan may still be in use
+    bool ok = true;
+    sc.d_idx = upload(h, sc.plan.idx, ok);
+    sc.d_caches = dalloc(h, sc.plan.cache_total, ok, false);
+    if (!ok) return fail("cb200_scatter_plan: device allocation failed");
+    return 0;
+}
+
+extern "C" void *cb200_scatter_buffer(cb200_handle *h, int which)
+{
+    const int slot = scatter_slot(which);
+    return slot < 0 ? nullptr : (void *)h->scatter[slot].d_caches;
+}
+
+extern "C" int cb200_scatter(cb200_handle *h, int which, const double *caches_host, int first, int count)
+{
+    NEED_KKT();
+    const int slot = scatter_slot(which);
+    if (slot < 0 || !h->scatter[slot].d_idx) return fail("cb200_scatter: no scatter plan for this array");
+    if (check_array(h, which, first, count)) return -1;
+    if (count == 0) return 0;
+    const cb200_handle::Scatter &sc = h->scatter[slot];
+    const ArrayDesc &a = h->arr[which];
+    CUDA_OK(cudaSetDevice(h->device));
+    if (caches_host)
+        CUDA_OK(cudaMemcpyAsync(sc.d_caches + (long long)first * sc.plan.cache_total, caches_host,
+                                sizeof(double) * sc.plan.cache_total * count, cudaMemcpyHostToDevice, h->stream));
+    if (sc.plan.nnz > 0) {
+        const int chunks = std::max(1, std::min((sc.plan.nnz + 1023) / 1024, 64));     // four entries per thread or more
+        for (int c0 = 0; c0 < count; c0 += 65535) {       // gridDim.y limit
+            k_scatter<<<dim3(chunks, std::min(count - c0, 65535)), 256, 0, h->stream>>>(
+                sc.plan.nnz, sc.plan.ncaches, sc.d_idx, sc.d_caches, sc.plan.cache_total, a.ptr, a.len, first + c0);
+            CUDA_OK(cudaGetLastError());
+        }
+    }
+    if (which == CB200_W_VALUES || which == CB200_G_VALUES) h->values_dirty = true;
+    return 0;
 }
 
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host)

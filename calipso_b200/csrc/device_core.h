@@ -441,6 +441,23 @@ CB_DEVN void expand_values(const Ctx &ctx, const DevProblem &P, const Inst &I)
     ctx.sync();
 }
 
+// evaluate!'s cache scatter as a gather (plan: host_setup.h ScatterPlan): out[e] = sum over the caches, in order, of the
+// last cache entry written to pattern entry e (0.0 where a cache has none) -- the dense-matrix `=` scatter of
+// src/solver/evaluate.jl:39-41,75-77,111-113 followed by the sum of residual_jacobian_variables.jl:11-13.
+CB_DEV void scatter_caches(const Ctx &ctx, int nnz, int ncaches, const int *__restrict__ idx,
+                           const double *__restrict__ cache, double *__restrict__ out, int first, int stride)
+{
+    for (int e = first + ctx.tid; e < nnz; e += stride) {
+        const int i0 = idx[e];
+        double v = i0 >= 0 ? cache[i0] : 0.0;
+        for (int c = 1; c < ncaches; c++) {
+            const int i = idx[(long long)c * nnz + e];
+            v += i >= 0 ? cache[i] : 0.0;
+        }
+        out[e] = v;
+    }
+}
+
 // The entries of the reduced matrix K that are not plain copies of W, G, C values:
 // kx = [W diagonal + eps_p | y diagonal | nonnegative z diagonal | upper triangles of the second-order z blocks].
 // eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.  The matrix itself

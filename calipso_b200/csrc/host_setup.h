@@ -186,6 +186,45 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.leaf_e_off = up(S.leaf_e_off); P.leaf_e_col = up(S.leaf_e_col); P.leaf_e_pos = up(S.leaf_e_pos);
 }
 
+// evaluate!'s scatter of the flat derivative caches (src/solver/evaluate.jl:37-42,55-60,73-78,95-100,109-114) turned
+// into a gather.  The reference writes cache entry i to the dense matrix at sparsity[i] with `=`: where keys repeat
+// (stage sparsities overlap: trajectory_optimization/methods.jl:26,41) the LAST entry wins; absent keys stay 0.0.  For
+// `which` = W the caches are (objective, equality-dual, cone-dual) and the three matrices are then added in that order
+// (residual_jacobian_variables.jl:11-13); G and C have one cache.  The plan holds, per cache and per entry of the
+// pattern, the position (in the concatenated caches) of the last entry with that key, or -1.  Keys of W below the
+// diagonal are dropped (the path reads the upper triangle only, linear_solver.jl:23); any other key outside the
+// pattern is an error.
+struct ScatterPlan {
+    int ncaches = 0, nnz = 0;
+    long long cache_total = 0;
+    std::vector<int> idx;      // [ncaches][nnz]
+
+    std::string build(int nrows, int ncols, const int *cp, const int *ri, bool upper_only, int ncaches_,
+                      const int *cache_len, const int *rows, const int *cols)
+    {
+        ncaches = ncaches_; nnz = cp[ncols]; cache_total = 0;
+        if (ncaches < 1 || ncaches > 3) return "scatter plan: 1 to 3 caches";
+        idx.assign((size_t)ncaches * nnz, -1);
+        long long off = 0;
+        for (int c = 0; c < ncaches; c++) {
+            if (cache_len[c] < 0) return "scatter plan: negative cache length";
+            for (int e = 0; e < cache_len[c]; e++) {
+                const int r = rows[off + e], col = cols[off + e];
+                if (r < 0 || r >= nrows || col < 0 || col >= ncols) return "scatter plan: key out of range";
+                if (upper_only && r > col) continue;
+                const int *lo = ri + cp[col], *hi = ri + cp[col + 1];
+                const int *it = std::lower_bound(lo, hi, r);
+                if (it == hi || *it != r) return "scatter plan: key (" + std::to_string(r) + "," + std::to_string(col) + ") is not in the pattern";
+                idx[(size_t)c * nnz + (it - ri)] = (int)(off + e);      // later entries overwrite: last write wins
+            }
+            off += cache_len[c];
+        }
+        if (off > 0x7fffffffLL) return "scatter plan: caches too long";
+        cache_total = off;
+        return "";
+    }
+};
+
 template <class Up> void fill_problem(DevProblem &P, const HostProblem &H, Up up)
 {
     P.n = H.n; P.m = H.m; P.p = H.p; P.total = H.total; P.q_nn = H.q_nn; P.nsoc = H.nsoc; P.tri_total = H.tri_total;

@@ -225,6 +225,27 @@ class BatchKKT:
         S = np.transpose(out, (0, 2, 1))
         return S[0] if np.ndim(jacobian_parameters) == 2 else S
 
+    def scatter_plan(self, name, sparsities):
+        """The gather plan for evaluate!'s `=` scatter of the flat derivative caches (src/solver/evaluate.jl:37-42,55-60,
+        73-78,95-100,109-114).  name: "W_VALUES" (sparsities = up to three key lists: objective, equality-dual,
+        cone-dual Hessian caches), "G_VALUES" or "C_VALUES" (one key list).  A key list is a sequence of 0-based
+        (row, col) pairs in cache order -- the reference's `*_sparsity` vectors; repeated keys: the last entry wins."""
+        lens = i32([len(sp) for sp in sparsities])
+        keys = [np.asarray(sp, dtype=np.int64).reshape(-1, 2) for sp in sparsities]
+        allk = np.concatenate(keys, axis=0) if keys else np.zeros((0, 2), np.int64)
+        rows, cols = i32(allk[:, 0]), i32(allk[:, 1])
+        self.b.check(self.lib.cb200_scatter_plan(self.h, A[name], len(lens), ip(lens), ip(rows), ip(cols)))
+        self._scatter_len = getattr(self, "_scatter_len", {})
+        self._scatter_len[name] = int(lens.sum())
+
+    def scatter(self, name, caches, first=0):
+        """Scatter the flat caches ([count, sum of cache lengths], the caches of one instance concatenated in plan order)
+        into the value array `name` of instances first .. first+count-1."""
+        L = self._scatter_len[name]
+        v = f64(caches).reshape(-1, L) if L > 0 else np.zeros((np.shape(caches)[0] if np.ndim(caches) > 1 else 1, 0))
+        self.b.check(self.lib.cb200_scatter(self.h, A[name], dp(v) if L > 0 else None, first, v.shape[0]))
+        self.b.check(self.lib.cb200_synchronize(self.h))   # the source buffer may be a temporary
+
     def jacobian_times(self, v):
         v = f64(v).reshape(self.batch, self.total)
         out = np.zeros_like(v)

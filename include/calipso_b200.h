@@ -189,6 +189,22 @@ int cb200_kkt_factor_solve(cb200_handle *h, int nsolves);
  * jacobian_parameters[b][i][total] (column i contiguous), sensitivity[b][i][total]. */
 int cb200_differentiate(cb200_handle *h, int num_parameters, const double *jacobian_parameters_host,
                         double *sensitivity_host);
+/* evaluate!'s scatter of the flat derivative caches, src/solver/evaluate.jl:37-42,
+ * 73-78, 109-114 (Hessian caches) and :55-60, 95-100 (Jacobian caches): the reference writes cache entry i into a
+ * dense matrix at key sparsity[i] with `=` -- where keys repeat (overlapping stage sparsities of the trajectory
+ * optimisation front end, trajectory_optimization/methods.jl:26,41) the LAST entry wins, absent
+ * keys stay 0.0 -- and, for the Hessian, adds the objective, equality-dual and cone-dual matrices in that order
+ * (residual_jacobian_variables.jl:11-13).  cb200_scatter_plan turns that into a gather list, once per sparsity:
+ *   which = CB200_W_VALUES: ncaches = 1..3 caches (objective, equality-dual, cone-dual); keys below the diagonal are
+ *           dropped (the path reads the upper triangle, linear_solver.jl:23);
+ *   which = CB200_G_VALUES / CB200_C_VALUES: one cache (equality / cone Jacobian).
+ * cache_len[ncaches]; rows/cols = the keys of all caches, concatenated, 0-based.  A key outside the pattern given to
+ * cb200_create is an error.  cb200_scatter copies caches_host ([count][sum cache_len], instance-major; NULL = the
+ * caller already wrote the device buffer cb200_scatter_buffer(h, which), laid out [batch][sum cache_len]) and fills
+ * the value array `which` of instances first .. first+count-1 on the handle's stream (asynchronous). */
+int cb200_scatter_plan(cb200_handle *h, int which, int ncaches, const int *cache_len, const int *rows, const int *cols);
+int cb200_scatter(cb200_handle *h, int which, const double *caches_host, int first_instance, int count);
+void *cb200_scatter_buffer(cb200_handle *h, int which);
 /* out = J v for instance-major v (mul! with jacobian_variables, iterative_refinement.jl:9) -- tests / glue */
 int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host);
 

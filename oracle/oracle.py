@@ -460,3 +460,32 @@ def from_problem(P, perm=None, options=None) -> Oracle:
     if getattr(P, "W_val", None) is not None:
         o.set_lq(P.W_val, P.G_val, P.C_val, P.q, P.g0, P.h0)
     return o
+
+
+# ---------------------------------------------------------------------------------------------------- evaluate!'s scatter
+def scatter_dense(shape, sparsity, cache):
+    """src/solver/evaluate.jl:39-41 (and :57-59, 75-77, 97-99, 111-113), restated literally: a dense matrix that starts at
+    zero (problem_data.jl) and receives `M[idx...] = cache[i]` in cache order -- a repeated key keeps the LAST value.
+    sparsity: 0-based (row, col) pairs."""
+    M = np.zeros(shape)
+    for i, (r, c) in enumerate(sparsity):
+        M[r, c] = cache[i]
+    return M
+
+
+def lagrangian_hessian_dense(n, sparsities, caches):
+    """residual_jacobian_variables.jl:9-15: H[i, j] = objective_xx[i, j]; H[i, j] += equality_dual_xx[i, j];
+    H[i, j] += cone_dual_xx[i, j] on the dense matrices scatter_dense produced (missing caches count as zero matrices)."""
+    H = scatter_dense((n, n), sparsities[0], caches[0])
+    for sp, ca in zip(sparsities[1:], caches[1:]):
+        H = H + scatter_dense((n, n), sp, ca)
+    return H
+
+
+def values_at_pattern(M, colptr, rowval):
+    """The entries of dense M at a CSC pattern (what the hot path reads)."""
+    out = np.zeros(len(rowval))
+    for j in range(len(colptr) - 1):
+        for k in range(colptr[j], colptr[j + 1]):
+            out[k] = M[rowval[k], j]
+    return out

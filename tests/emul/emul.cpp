@@ -29,6 +29,7 @@ struct cb200_handle {
     std::vector<double> scratch;
     long long ksize = 0;
     const Symbolic &sym() const { return generic ? gsym : hp.sym; }
+    struct Scatter { ScatterPlan plan; std::vector<double> caches; bool set = false; } scatter[3];
 };
 
 enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_KX, X_LCSR, X_WF, X_GR, X_COUNT };
@@ -301,6 +302,45 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H,
             for (int k = 0; k < P.total; k++) out[k] = -1.0 * out[k];
         }
     END_FOR
+    return 0;
+}
+static int scatter_slot(int which)
+{
+    return which == CB200_W_VALUES ? 0 : which == CB200_G_VALUES ? 1 : which == CB200_C_VALUES ? 2 : -1;
+}
+extern "C" int cb200_scatter_plan(cb200_handle *h, int which, int ncaches, const int *cache_len, const int *rows, const int *cols)
+{
+    if (h->generic) return fail("not available on a LinearSolver-seam handle");
+    const int slot = scatter_slot(which);
+    if (slot < 0) return fail("cb200_scatter_plan: which must be CB200_W_VALUES, CB200_G_VALUES or CB200_C_VALUES");
+    if (slot > 0 && ncaches != 1) return fail("cb200_scatter_plan: the G and C values have one cache each");
+    const HostProblem &H = h->hp;
+    auto &sc = h->scatter[slot];
+    std::string err = slot == 0 ? sc.plan.build(H.n, H.n, H.Wp.data(), H.Wi.data(), true, ncaches, cache_len, rows, cols)
+                    : slot == 1 ? sc.plan.build(H.m, H.n, H.Gp.data(), H.Gi.data(), false, ncaches, cache_len, rows, cols)
+                                : sc.plan.build(H.p, H.n, H.Cp.data(), H.Ci.data(), false, ncaches, cache_len, rows, cols);
+    if (!err.empty()) { sc.plan = ScatterPlan(); sc.set = false; return fail(err); }
+    sc.caches.assign((size_t)std::max<long long>(sc.plan.cache_total * h->batch, 1), 0.0);
+    sc.set = true;
+    return 0;
+}
+extern "C" void *cb200_scatter_buffer(cb200_handle *h, int which)
+{
+    const int slot = scatter_slot(which);
+    return slot < 0 || !h->scatter[slot].set ? nullptr : (void *)h->scatter[slot].caches.data();
+}
+extern "C" int cb200_scatter(cb200_handle *h, int which, const double *caches_host, int first, int count)
+{
+    const int slot = scatter_slot(which);
+    if (h->generic || slot < 0 || !h->scatter[slot].set) return fail("cb200_scatter: no scatter plan for this array");
+    if (check(h, which, first, count)) return -1;
+    auto &sc = h->scatter[slot];
+    const long long L = sc.plan.cache_total;
+    if (caches_host) memcpy(sc.caches.data() + first * L, caches_host, sizeof(double) * L * count);
+    Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr};
+    for (int b = first; b < first + count; b++)
+        scatter_caches(ctx, sc.plan.nnz, sc.plan.ncaches, sc.plan.idx.data(), sc.caches.data() + b * L,
+                       h->arr[which].data() + (long long)b * h->len[which], 0, 1);
     return 0;
 }
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v, double *out)

@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 
 from calipso_b200 import lqc  # noqa: E402
 
+LOCKSTEP = os.environ.get("CB200_LQ_LOCKSTEP", "0") not in ("", "0")   # one k_lq_step launch per Newton iteration (A/B)
+
 CFG = dict(T=40, n_x=36, n_u=12, n_soc=100)       # BASELINE.json configs[3] (cfg3)
 METRIC = "newton_iterations_per_second"
 UNIT = "Newton it/s"
@@ -256,8 +258,10 @@ def run_gpu(args):
         ev[1].record(stream)
         ev[1].synchronize()
         lq_ms[0] += ev[0].elapsed_time(ev[1])
-        launches[0] += 1 + r["steps"] + (r["steps"] + args.check_every - 1) // args.check_every
-        launches[1] += r["steps"]
+        checks = (r["steps"] + args.check_every - 1) // args.check_every
+        lq = r["steps"] if LOCKSTEP else checks     # fused: one k_lq_step launch carries a whole check interval
+        launches[0] += 1 + lq + checks              # k_lq_begin + k_lq_step + k_count_states
+        launches[1] += lq
         return r
 
     for _ in range(args.warmup):
@@ -317,7 +321,13 @@ def run_gpu(args):
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     kkt_achieved = b_unit * B / (ms_kkt * 1e-3) / 1e9
     tpath2 = os.path.join(ROOT, "profiles", "lq_step_traffic.json")
-    traffic = json.load(open(tpath2)).get("dram_bytes_per_launch") if os.path.exists(tpath2) else None
+    # measured DRAM bytes of one Newton iteration of one instance (ncu capture of a launch in which every instance ran
+    # exactly one iteration), scaled to the Newton iterations an average launch of the timed region carried
+    traffic = None
+    if os.path.exists(tpath2):
+        per_it = json.load(open(tpath2)).get("dram_bytes_per_instance_iteration")
+        if per_it:
+            traffic = per_it * args.steps * iters_per_solve / max(n_lq_launches, 1)
     tpath = os.path.join(ROOT, "profiles", "kkt_factor_solve_traffic.json")
     kkt_traffic = json.load(open(tpath)).get("dram_bytes_per_instance") * B if os.path.exists(tpath) else None   # capture at batch 444, scaled
     achieved = newton_bytes / max(n_lq_launches, 1) / (ms_lq_launch * 1e-3) / 1e9
@@ -326,9 +336,11 @@ def run_gpu(args):
                     algorithmic_bytes_per_launch=newton_bytes / max(n_lq_launches, 1),
                     algorithmic_bytes_formula="SURVEY 8(d): n_fact*(B_asm+B_factor) + n_solves*(B_solve+B_spmv) + n_newton*(B_res+B_cone)",
                     factorizations=d_fact, reduced_solves=d_solv, peak_source=peak_src,
+                    newton_iterations_per_launch=args.steps * iters_per_solve / max(n_lq_launches, 1),
                     note="launch duration = CUDA events around cb200_lq_solve on the handle's stream / k_lq_step launches "
-                         "(includes the per-check 32-byte counter read-back); converged instances are masked, so late "
-                         "launches carry fewer bytes",
+                         "(includes the per-check 32-byte counter read-back); one launch carries up to check_every Newton "
+                         "iterations of every instance, a CTA leaves when its instance has converged; traffic = ncu DRAM "
+                         "bytes per instance-iteration (profiles/lq_step_traffic.json) x iterations per launch",
                     kkt_solve=dict(kernel="k_kkt_factor_solve", achieved=kkt_achieved, frac=kkt_achieved / peak,
                                    algorithmic_bytes_per_kkt_solve=b_unit, kkt_solves_per_launch=B, ms_per_launch=ms_kkt,
                                    kkt_solve_ms_per_instance_batched=ms_kkt / B, traffic=kkt_traffic,
@@ -455,6 +467,9 @@ def run_gpu(args):
                                 nnz_K_upper=info["nnzK"], nnz_L=info["nnzL"], supernodes=info["supernodes"],
                                 levels=info["levels"], batch_per_gpu=B, distinct_seeds_per_gpu=distinct,
                                 newton_iterations_per_step=total_iters,
+                                newton_iterations_per_launch_max=args.check_every,
+                                schedule="lock-step (one launch per Newton iteration)" if LOCKSTEP else
+                                         "independent (a launch carries up to check_every iterations of an instance)",
                                 l2_policy="inputs larger than L2: per-GPU working set = batch x ~4.5 MB",
                                 parallelism=f"instances sharded {B}/GPU, NCCL all-reduce of convergence counts only"),
                     e2e=e2e, gpu_launches=gpu_launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks,
@@ -473,7 +488,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1332, help="instances per GPU (9 per SM: three waves of 3 resident CTAs x 148 SMs)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct seeds per GPU, tiled over the batch")
     ap.add_argument("--max-newton", type=int, default=400)
-    ap.add_argument("--check-every", type=int, default=4)
+    ap.add_argument("--check-every", type=int, default=400,
+                    help="Newton iterations per k_lq_step launch / convergence check (default: run every instance to "
+                         "convergence inside one launch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")

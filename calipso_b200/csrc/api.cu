@@ -168,10 +168,16 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_begin(const __gr
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o, int iterations)
 {
     KERNEL_PROLOGUE
-    solve_step_lq(ctx, P, I, o);
+    // `iterations` Newton iterations of this instance inside one launch: instances are independent, so nothing forces
+    // them into lock-step -- a CTA whose instance converges (or fails) leaves at once and the next instance of the batch
+    // takes its place on the SM instead of waiting for the slowest instance of every iteration
+    for (int k = 0; k < iterations; k++) {
+        solve_step_lq(ctx, P, I, o);             // (ends with a CTA barrier: the state below is uniform)
+        if (I.istat[I_CONVERGED] != 0) break;
+    }
     PROF_FLUSH(I.prof);
 }
 
@@ -673,7 +679,15 @@ extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
 {
     NEED_KKT();
     FRESH_VALUES();
-    for (int k = 0; k < iterations; k++) LAUNCH_SMEM(k_lq_step, h->P, h->B, h->opt);
+    // one launch carries all `iterations` passes of an instance (CB200_LQ_LOCKSTEP=1: one launch per pass, every instance
+    // in lock-step -- the same arithmetic; kept for A/B timing)
+    const char *ls = getenv("CB200_LQ_LOCKSTEP");
+    const bool lockstep = ls && atoi(ls) != 0;
+    if (lockstep) {
+        for (int k = 0; k < iterations; k++) LAUNCH_SMEM(k_lq_step, h->P, h->B, h->opt, 1);
+    } else if (iterations > 0) {
+        LAUNCH_SMEM(k_lq_step, h->P, h->B, h->opt, iterations);
+    }
     return 0;
 }
 extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); FRESH_VALUES(); LAUNCH_SMEM(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }

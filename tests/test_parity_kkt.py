@@ -250,3 +250,30 @@ def test_errors_are_reported(backend):
     k = BatchKKT(P, binding=b)
     with pytest.raises(Exception):
         k.get("RHS")                                           # LinearSolver-seam array on a KKT handle
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make,batch,check_every", [(lqc.tiny, 5, 3), (lqc.cfg2, 3, 4), (lqc.cfg2, 3, 400)])
+def test_independent_launch_schedule_is_bitwise_the_lockstep_one(make, batch, check_every, monkeypatch):
+    """cb200_lq_solve: a launch that carries several Newton iterations of an instance (default) computes exactly what
+    one launch per iteration computes (CB200_LQ_LOCKSTEP=1) -- instances never interact, only the scheduling differs."""
+    from calipso_b200.solver import BatchKKT
+    Ps = [make(i) for i in range(batch)]
+    out = []
+    for lockstep in ("1", "0"):
+        monkeypatch.setenv("CB200_LQ_LOCKSTEP", lockstep)
+        k = BatchKKT(Ps[0], batch=batch, binding=backends.binding("cuda"))
+        k.load_lq(Ps)
+        k.initialize(np.stack([P.x0 for P in Ps]))
+        k.lq_begin()
+        r = k.lq_solve(max_steps=400, check_every=check_every)
+        st = k.stats()
+        out.append((r["converged"], k.get("POINT"), k.get("DUAL"), k.get("SCALARS"),
+                    {n: st[n].copy() for n in ("total_iterations", "factorizations", "solves", "fallbacks")}))
+        k.close()
+    a, b = out
+    assert a[0] == b[0] == batch
+    for i in (1, 2, 3):
+        assert np.array_equal(a[i], b[i])
+    for n in a[4]:
+        assert np.array_equal(a[4][n], b[4][n]), n

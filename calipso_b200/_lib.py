@@ -81,6 +81,7 @@ SYMBOLS = {
     "cb200_get_factor": (C.c_int, [vp, C.c_int, c_ip, c_ip, c_dp, c_dp]),
     "cb200_set_array": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
     "cb200_get_array": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
+    "cb200_initialize": (C.c_int, [vp, c_dp, C.c_int, C.c_int]),
     "cb200_get_stats": (C.c_int, [vp, c_ip, C.c_int, C.c_int]),
     "cb200_get_array_async": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
     "cb200_get_stats_async": (C.c_int, [vp, c_ip, C.c_int, C.c_int]),

@@ -557,6 +557,19 @@ extern "C" int cb200_set_array(cb200_handle *h, int which, const double *host, i
     return 0;
 }
 
+extern "C" int cb200_initialize(cb200_handle *h, const double *guess_host, int first, int count)
+{
+    if (h->generic) return fail("not available on a LinearSolver-seam handle");
+    if (check_array(h, CB200_POINT, first, count)) return -1;
+    if (count == 0) return 0;
+    CUDA_OK(cudaSetDevice(h->device));
+    const ArrayDesc &a = h->arr[CB200_POINT];
+    const size_t row = sizeof(double) * (size_t)h->hp.n;
+    CUDA_OK(cudaMemcpy2DAsync(a.ptr + (long long)first * a.len, sizeof(double) * a.len, guess_host, row, row, count,
+                              cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
 extern "C" int cb200_get_array(cb200_handle *h, int which, double *host, int first, int count)
 {
     if (check_array(h, which, first, count)) return -1;

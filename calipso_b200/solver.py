@@ -266,9 +266,9 @@ class BatchKKT:
         g = f64(guesses).reshape(-1, self.n)
         if g.shape[0] == 1 and self.batch > 1:
             g = np.repeat(g, self.batch, axis=0)
-        w = self.get("POINT")
-        w[:, :self.n] = g
-        self.set("POINT", w)
+        assert g.shape[0] == self.batch
+        self.b.check(self.lib.cb200_initialize(self.h, dp(g), 0, self.batch))     # the primal block only
+        self.b.check(self.lib.cb200_synchronize(self.h))   # the source buffer may be a temporary
 
     def lq_evaluate(self, flags, at_candidate=False):
         self.b.check(self.lib.cb200_lq_evaluate(self.h, flags, int(at_candidate)))

@@ -140,6 +140,10 @@ int cb200_get_factor(cb200_handle *h, int instance, int *Lp, int *Li, double *Lx
 /* ------------------------------------------------------------------------------------------------ data movement */
 int cb200_set_array(cb200_handle *h, int which, const double *host, int first_instance, int count); /* H2D, async */
 int cb200_get_array(cb200_handle *h, int which, double *host, int first_instance, int count);       /* D2H + sync */
+/* initialize!(solver, guess), src/solver/initialize.jl:9-13: solution.variables .= guess for instances first .. first+count-1
+ * (guess_host = [count][n]; H2D of the primal block only, asynchronous; slacks and duals are set by the caller or by
+ * cb200_lq_begin as initialize_slacks! / initialize_duals! do, initialize.jl:15-36) */
+int cb200_initialize(cb200_handle *h, const double *guess_host, int first_instance, int count);
 int cb200_get_stats(cb200_handle *h, int *host /* [count][CB200_I_COUNT] */, int first_instance, int count);
 /* the same without the final stream synchronisation (host buffers should be pinned; call cb200_synchronize before reading
  * them): lets several handles, each on its own stream, overlap their copies with each other's kernels */
@@ -211,7 +215,10 @@ int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host
 /* LQ-conic family with on-device callbacks: the whole of solve! stays on the GPU */
 int cb200_lq_evaluate(cb200_handle *h, int flags, int at_candidate);   /* evaluate!, evaluate.jl:1-124 */
 int cb200_lq_begin(cb200_handle *h, int warmstart);                    /* solve.jl:8-95 */
-int cb200_lq_step(cb200_handle *h, int iterations);                    /* `iterations` passes of solve.jl:98-368 */
+/* up to `iterations` passes of solve.jl:98-368 per instance in ONE launch: instances are independent, a converged (or
+ * failed) instance stops early and frees its place on the SM.  (CB200_LQ_LOCKSTEP=1 in the environment: one launch per
+ * pass, all instances in lock-step -- bitwise the same results, for A/B timing.) */
+int cb200_lq_step(cb200_handle *h, int iterations);
 /* run until every instance converged / gave up or max_steps passes; with an NCCL communicator attached the
  * termination test is the all-reduced count over ranks.  counts[4] = running, converged, gave up, error (global). */
 int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, long long *counts, int *steps_done);

@@ -192,6 +192,15 @@ extern "C" int cb200_set_array(cb200_handle *h, int which, const double *host, i
     memcpy(h->arr[which].data() + (long long)first * h->len[which], host, sizeof(double) * h->len[which] * count);
     return 0;
 }
+extern "C" int cb200_initialize(cb200_handle *h, const double *guess, int first, int count)
+{
+    if (h->generic) return fail("not available on a LinearSolver-seam handle");
+    if (check(h, CB200_POINT, first, count)) return -1;
+    const long long len = h->len[CB200_POINT];
+    for (int b = 0; b < count; b++)
+        memcpy(h->arr[CB200_POINT].data() + (first + b) * len, guess + (long long)b * h->hp.n, sizeof(double) * h->hp.n);
+    return 0;
+}
 extern "C" int cb200_get_array(cb200_handle *h, int which, double *host, int first, int count)
 {
     if (check(h, which, first, count)) return -1;

@@ -74,3 +74,29 @@ def test_async_readback_equals_blocking_readback():
     assert np.array_equal(out, ref)
     assert np.array_equal(st[:, _lib.I["total_iterations"]], k.stats()["total_iterations"])
     assert b.lib.cb200_values_changed(k.h) == 0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("backend", backends.BACKENDS)
+def test_initialize_writes_the_primal_block_only(backend):
+    """cb200_initialize = initialize!(solver, guess), initialize.jl:9-13: solution.variables .= guess, nothing else."""
+    import numpy as np
+    from calipso_b200 import lqc
+    from calipso_b200.solver import BatchKKT
+    P = lqc.tiny()
+    k = BatchKKT(P, batch=4, binding=backends.binding(backend))
+    rng = np.random.default_rng(0)
+    w0 = rng.standard_normal((4, k.total))
+    k.set("POINT", w0)
+    g = rng.standard_normal((4, k.n))
+    k.initialize(g)
+    w = k.get("POINT")
+    assert np.array_equal(w[:, :k.n], g) and np.array_equal(w[:, k.n:], w0[:, k.n:])
+    g2 = rng.standard_normal((2, k.n))                       # a sub-range of the batch through the C ABI
+    k.b.check(k.lib.cb200_initialize(k.h, _lib.dp(_lib.f64(g2)), 1, 2))
+    w2 = k.get("POINT")
+    assert np.array_equal(w2[1:3, :k.n], g2) and np.array_equal(w2[[0, 3]], w[[0, 3]])
+    with pytest.raises(_lib.CalipsoB200Error):
+        k.b.check(k.lib.cb200_initialize(k.h, _lib.dp(_lib.f64(g2)), 3, 2))

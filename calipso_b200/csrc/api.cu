@@ -751,9 +751,16 @@ extern "C" int cb200_scatter_plan(cb200_handle *h, int which, int ncaches, const
     std::string err = slot == 0 ? sc.plan.build(H.n, H.n, H.Wp.data(), H.Wi.data(), true, ncaches, cache_len, rows, cols)
                     : slot == 1 ? sc.plan.build(H.m, H.n, H.Gp.data(), H.Gi.data(), false, ncaches, cache_len, rows, cols)
                                 : sc.plan.build(H.p, H.n, H.Cp.data(), H.Ci.data(), false, ncaches, cache_len, rows, cols);
-    if (!err.empty()) { sc.plan = ScatterPlan(); return fail(err); }
     CUDA_OK(cudaSetDevice(h->device));
     CUDA_OK(cudaStreamSynchronize(h->stream));      // a previous plan may still be in use
+    for (void *old : {(void *)sc.d_idx, (void *)sc.d_caches})      // a new plan replaces the previous one
+        if (old) {
+            h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), old), h->allocs.end());
+            cudaFree(old);
+        }
+    sc.d_idx = nullptr;
+    sc.d_caches = nullptr;
+    if (!err.empty()) { sc.plan = ScatterPlan(); return fail(err); }
     bool ok = true;
     sc.d_idx = upload(h, sc.plan.idx, ok);
     sc.d_caches = dalloc(h, sc.plan.cache_total, ok, false);

@@ -179,3 +179,25 @@ def test_scatter_errors(backend):
         k.scatter_plan("G_VALUES", [gc, gc])
     with pytest.raises(_lib.CalipsoB200Error):
         k.scatter_plan("POINT", [[(0, 0)]])
+
+
+@pytest.mark.parametrize("backend", backends.BACKENDS)
+def test_a_new_plan_replaces_the_previous_one(backend):
+    rng = np.random.default_rng(8)
+    (Wp, Wi, Gp, Gi), wc, gc = random_case(rng, 10, 4)
+    k = BatchKKT(_Pattern(10, 4, Wp, Wi, Gp, Gi), batch=2, binding=backends.binding(backend))
+    for caches in (wc, wc[:1], [wc[1], wc[0]]):
+        k.scatter_plan("W_VALUES", caches)
+        vals = rng.standard_normal((2, sum(len(c) for c in caches)))
+        k.scatter("W_VALUES", vals)
+        W = k.get("W_VALUES")
+        offs = np.cumsum([0] + [len(c) for c in caches])
+        for b in range(2):
+            upper = [[(r, c) for (r, c) in ks if r <= c] for ks in caches]
+            uvals = [[vals[b][offs[q] + i] for i, (r, c) in enumerate(ks) if r <= c] for q, ks in enumerate(caches)]
+            H = orc.lagrangian_hessian_dense(10, upper, uvals)
+            assert np.array_equal(W[b], orc.values_at_pattern(H, Wp, Wi))
+    with pytest.raises(_lib.CalipsoB200Error):                       # a failed plan leaves no plan behind
+        k.scatter_plan("W_VALUES", [[(0, 10)]])
+    with pytest.raises(_lib.CalipsoB200Error, match="no scatter plan"):
+        k.scatter("W_VALUES", vals)

@@ -213,6 +213,33 @@ def test1() -> DenseNLP:
         hess_hz=lambda x, z: _z(n, n), x0=np.ones(n))
 
 
+def test2(seed=0) -> DenseNLP:
+    """test/solver/test2.jl:1-32: bilinear objective, one quadratic and one linear inequality (x0 = rand(2), seeded)."""
+    rng = np.random.default_rng(seed)
+    return DenseNLP(
+        "test2", 2, 0, 2, 2, np.zeros(0, np.int32),
+        f=lambda x: -x[0] * x[1] + 2.0 / (3.0 * np.sqrt(3.0)), grad=lambda x: np.array([-x[1], -x[0]]),
+        hess=lambda x: np.array([[0.0, -1.0], [-1.0, 0.0]]), g=lambda x: _z(0), jac_g=lambda x: _z(0, 2),
+        hess_gy=lambda x, y: _z(2, 2),
+        h=lambda x: np.array([-x[0] - x[1] ** 2 + 1.0, x[0] + x[1]]),
+        jac_h=lambda x: np.array([[-1.0, -2.0 * x[1]], [1.0, 1.0]]),
+        hess_hz=lambda x, z: z[0] * np.array([[0.0, 0.0], [0.0, -2.0]]), x0=rng.random(2))
+
+
+def test3(seed=0) -> DenseNLP:
+    """test/solver/test3.jl:1-32: Rosenbrock objective with a cubic and a linear inequality (x0 = rand(2), seeded)."""
+    rng = np.random.default_rng(seed)
+    return DenseNLP(
+        "test3", 2, 0, 2, 2, np.zeros(0, np.int32),
+        f=lambda x: 100.0 * (x[1] - x[0] ** 2) ** 2 + (1.0 - x[0]) ** 2,
+        grad=lambda x: np.array([-400.0 * x[0] * (x[1] - x[0] ** 2) - 2.0 * (1.0 - x[0]), 200.0 * (x[1] - x[0] ** 2)]),
+        hess=lambda x: np.array([[1200.0 * x[0] ** 2 - 400.0 * x[1] + 2.0, -400.0 * x[0]], [-400.0 * x[0], 200.0]]),
+        g=lambda x: _z(0), jac_g=lambda x: _z(0, 2), hess_gy=lambda x, y: _z(2, 2),
+        h=lambda x: np.array([-(x[0] - 1.0) ** 3 + x[1] - 1.0, -x[0] - x[1] + 2.0]),
+        jac_h=lambda x: np.array([[-3.0 * (x[0] - 1.0) ** 2, 1.0], [-1.0, -1.0]]),
+        hess_hz=lambda x, z: z[0] * np.array([[-6.0 * (x[0] - 1.0), 0.0], [0.0, 0.0]]), x0=rng.random(2))
+
+
 def test4(seed=0) -> DenseNLP:
     """test/solver/test4.jl:1-33: linear objective on the unit ball."""
     rng = np.random.default_rng(seed)

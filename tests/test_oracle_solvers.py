@@ -1,6 +1,6 @@
 """Known answers / stopping criteria of the reference's solver tests, reached by the oracle's solve! restatement.
 
-Mirrors test/solver/{wachter,maratos,knitro,friction_cone,portfolio,test1,test4}.jl: four stopping criteria at exit
+Mirrors test/solver/{wachter,maratos,knitro,friction_cone,portfolio,test1,test2,test3,test4}.jl: four stopping criteria at exit
 (e.g. wachter.jl:36-45) plus the known optima.
 """
 import itertools
@@ -53,8 +53,8 @@ def test_knitro():
     check_criteria(o)
 
 
-def test_test1_and_test4():
-    for P in (problems.test1(), problems.test4()):
+def test_test1_to_test4():
+    for P in (problems.test1(), problems.test2(), problems.test3(), problems.test4()):
         o, rc = solve(P)
         assert rc == 1
         check_criteria(o)

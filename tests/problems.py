@@ -251,13 +251,14 @@ def test4(seed=0) -> DenseNLP:
         x0=rng.random(3))
 
 
-def pendulum(seed: int = 0, horizon: int = 11) -> DenseNLP:
+def pendulum(seed: int = 0, horizon: int = 11, overwrite: bool = False) -> DenseNLP:
     """README.md:129-176 / test/examples/pendulum.jl (BASELINE cfg1): pendulum swing-up, implicit-midpoint dynamics,
     variables [x_1, u_1, ..., x_{T-1}, u_{T-1}, x_T] (trajectory_optimization/dynamics.jl:333-340), equalities ordered
     dynamics, then stage constraints (data.jl:51-55): n = 32, m = 24, p = 0 for T = 11.  The action guess is seeded
     (the README draws it with randn).  Derivatives written out; second derivatives are summed where stage sparsities
     overlap (what the reference's own Hessian test does, hessian_lagrangian.jl:296-302; SURVEY.md Appendix A.17 notes
-    that the reference's evaluate! overwrites instead -- that happens before the hot-path boundary)."""
+    that the reference's evaluate! overwrites instead -- that happens before the hot-path boundary; overwrite=True builds
+    the equality-dual Hessian that way, i.e. the matrices the reference's solve! actually iterates with)."""
     T, h = horizon, 0.05
     ml2, grav_l, damp = 0.25, 9.81 / 0.5, 0.1 / 0.25
     nx, nu = 2, 1
@@ -317,7 +318,10 @@ def pendulum(seed: int = 0, horizon: int = 11) -> DenseNLP:
             d2 = -0.25 * h * grav_l * np.sin(0.5 * (x[0] + y[0])) * y_[2 * t + 1]     # d^2 d2 / d(x1|y1)^2
             for a in (ix[t], ix[t + 1]):
                 for b in (ix[t], ix[t + 1]):
-                    H[a, b] += d2
+                    if overwrite:
+                        H[a, b] = d2      # evaluate!'s `=` scatter (src/solver/evaluate.jl:75-77): the later stage wins
+                    else:
+                        H[a, b] += d2
         return H
 
     rng = np.random.default_rng(seed)
@@ -329,4 +333,11 @@ def pendulum(seed: int = 0, horizon: int = 11) -> DenseNLP:
     P = DenseNLP("pendulum", n, m, 0, 0, np.zeros(0, dtype=np.int32), f, grad, hess, g, jac_g, hess_gy,
                  lambda v: np.zeros(0), lambda v: np.zeros((0, n)), lambda v, z: np.zeros((n, n)), x0)
     P.x_goal, P.ix = x_goal, ix
+    return P
+
+
+def pendulum_overwrite() -> DenseNLP:
+    """cfg1 with the reference's actual (last-write-wins) second-derivative scatter, SURVEY.md Appendix A.17."""
+    P = pendulum(overwrite=True)
+    P.name = "pendulum_overwrite"
     return P

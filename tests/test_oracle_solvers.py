@@ -90,9 +90,11 @@ def test_portfolio():
     assert np.abs(P.b - P.A @ o.solution[:P.n] - s).max() < 1e-4
 
 
-def test_pendulum_readme_quickstart():
-    """README.md:129-176 / test/examples/pendulum.jl:64-73 (BASELINE cfg1): converges, dynamics feasible, goal reached."""
-    P = problems.pendulum()
+@pytest.mark.parametrize("overwrite", [False, True])
+def test_pendulum_readme_quickstart(overwrite):
+    """README.md:129-176 / test/examples/pendulum.jl:64-73 (BASELINE cfg1): converges, dynamics feasible, goal reached --
+    with the summed second derivatives and with the reference's actual last-write-wins scatter (Appendix A.17)."""
+    P = problems.pendulum(overwrite=overwrite)
     o, rc = solve(P)
     assert rc == 1
     check_criteria(o)

@@ -1794,9 +1794,12 @@ CB_DEV double residual_error(const Ctx &ctx, const DevProblem &P, const Inst &I,
     ProfTimer pt{I.prof, 0};
     pt.start();
     jacobian_times(ctx, P, I, step, I.tmp);
-    PAR_FOR(i, P.total) I.err[i] = I.res[i] - I.tmp[i];
-    ctx.sync();
-    double r = scope_max(ctx, P.total, [&](int i) { return fabs(I.err[i]); });
+    // one pass: the difference is stored and its magnitude enters the (order-independent) maximum
+    double r = scope_max(ctx, P.total, [&](int i) {
+        const double e = I.res[i] - I.tmp[i];
+        I.err[i] = e;
+        return fabs(e);
+    });
     pt.stop(PROF_JTIMES);
     return r;
 }
@@ -1811,7 +1814,24 @@ CB_DEVN bool iterative_refinement(const Ctx &ctx, const DevProblem &P, const Ins
     while (iteration <= o.max_iterative_refinement) {
         if (rn <= o.iterative_refinement_tolerance && iteration >= o.min_iterative_refinement) { done = true; break; }
         direction_symmetric(ctx, P, I, I.err, I.corr);
+#if CB_ON_DEVICE
+        for (int i0 = ctx.tid; i0 < P.total; i0 += 4 * ctx.nthr) {      // four independent load pairs in flight
+            double a[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * ctx.nthr;
+                a[u] = i < P.total ? I.step[i] : 0.0;
+                c[u] = i < P.total ? I.corr[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * ctx.nthr;
+                if (i < P.total) I.step[i] = a[u] + c[u];
+            }
+        }
+#else
         PAR_FOR(i, P.total) I.step[i] += I.corr[i];
+#endif
         ctx.sync();
         rn = residual_error(ctx, P, I, I.step);
         iteration++;

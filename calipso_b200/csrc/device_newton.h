@@ -25,6 +25,9 @@ CB_DEVN void lq_evaluate(const Ctx &ctx, const DevProblem &P, const Inst &I, con
         grouped_rows<4>(
             ctx, n,
             [&](int i, int sub, int st) {
+#if CB_ON_DEVICE
+                if (st == 4) return sparse_dot4(I.Wf, nullptr, wc, x, wp[i], wp[i + 1], sub);     // same order, eight loads in flight
+#endif
                 double a = 0.0;
                 for (int k = wp[i] + sub; k < wp[i + 1]; k += st) a += I.Wf[k] * x[wc[k]];
                 return a;
@@ -44,6 +47,9 @@ CB_DEVN void lq_evaluate(const Ctx &ctx, const DevProblem &P, const Inst &I, con
         grouped_rows<4>(
             ctx, m,
             [&](int i, int sub, int st) {
+#if CB_ON_DEVICE
+                if (st == 4) return sparse_dot4(I.Gr, nullptr, gc, x, gp[i], gp[i + 1], sub);
+#endif
                 double a = 0.0;
                 for (int k = gp[i] + sub; k < gp[i + 1]; k += st) a += I.Gr[k] * x[gc[k]];
                 return a;
@@ -63,6 +69,9 @@ CB_DEVN void lq_evaluate(const Ctx &ctx, const DevProblem &P, const Inst &I, con
             grouped_rows<4>(
                 ctx, n,
                 [&](int j, int sub, int st) {
+#if CB_ON_DEVICE
+                    if (st == 4) return sparse_dot4(Gv, nullptr, gi, y, gp[j], gp[j + 1], sub);
+#endif
                     double a = 0.0;
                     for (int k = gp[j] + sub; k < gp[j + 1]; k += st) a += Gv[k] * y[gi[k]];
                     return a;

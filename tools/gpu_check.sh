@@ -1,7 +1,6 @@
 #!/bin/bash
+# Short GPU check: the parity suite, the smoke test, and the batched-solve timing (tools/lq_time.py).
 O=gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $O/r1g_pytest.log
-timeout 200 compute-sanitizer --tool memcheck python -m pytest tests/test_scatter.py -m gpu -x -q > $O/r1g_sanitizer_scatter.log 2>&1
-python tools/scatter_time.py 1332 > $O/r1g_scatter_time.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > $O/r1g_smoke.log 2>&1
-tail -2 $O/r1g_pytest.log; tail -4 $O/r1g_sanitizer_scatter.log; cat $O/r1g_scatter_time.log; tail -1 $O/r1g_smoke.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $O/r1m_pytest.log
+LQ_CONFIGS="0:400" timeout 60 python tools/lq_time.py 1332 64 > $O/r1m_lq_time.log 2>&1
+tail -2 $O/r1m_pytest.log; cat $O/r1m_lq_time.log

@@ -516,6 +516,35 @@ def solve(solver: Solver) -> bool:
     return False
 
 
+def residual_jacobian_parameters(n, m, p, objective_xp, equality_dual_xp, cone_dual_xp, equality_p, cone_p):
+    """residual_jacobian_parameters!(data, problem, idx), src/solver/residual_jacobian_parameters.jl:1-40: dR/dtheta
+    (total x num_parameters) from the parameter derivatives evaluate! produces -- rows of x: objective + equality-dual +
+    cone-dual cross derivatives (added in that order, :8-14), rows of y: equality Jacobian (:23-27), rows of z: cone
+    Jacobian (:30-34); the r, s, t rows stay zero.  Pass None for a block that does not exist."""
+    blocks = [b for b in (objective_xp, equality_dual_xp, cone_dual_xp, equality_p, cone_p) if b is not None]
+    ntheta = np.shape(blocks[0])[1]
+    H = np.zeros((n + 2 * m + 3 * p, ntheta))
+    for b in (objective_xp, equality_dual_xp, cone_dual_xp):
+        if b is not None:
+            H[:n] += f64(b)
+    if m and equality_p is not None:
+        H[n + m + p:n + 2 * m + p] = f64(equality_p)
+    if p and cone_p is not None:
+        H[n + 2 * m + p:n + 2 * m + 2 * p] = f64(cone_p)
+    return H
+
+
+def differentiate(solver: Solver, jacobian_parameters):
+    """differentiate!(solver), src/solver/differentiate.jl:1-61, at the point solve! stopped at: the reduced matrix is
+    rebuilt from the second-order data of the last evaluate! (the reference does not re-evaluate it either, :13-20) and
+    factored once; solution_sensitivity = -J^-1 dR/dtheta column by column (:35-57)."""
+    k = solver.kkt
+    k.set("POINT", solver.solution)
+    solver.jacobian_parameters = f64(jacobian_parameters)
+    solver.solution_sensitivity = k.differentiate(solver.jacobian_parameters)
+    return solver.solution_sensitivity
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 class Inertia:
     """src/solver/inertia.jl:1-5"""

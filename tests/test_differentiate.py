@@ -68,3 +68,63 @@ def test_batched_sensitivities(backend):
         for name in ("POINT", "DUAL", "SCALARS", "W_VALUES", "G_VALUES", "C_VALUES"):
             k1.set(name, k.get(name, first=b, count=1))
         assert np.array_equal(k1.differentiate(H[b]), S[b])
+
+
+def equality_qp(seed=0, n=10, m=5):
+    """test/solver/qp_equality.jl:1-40: 1/2 x'P x + p'x with P diagonal, A x = b; theta = [diag P; p; vec A; b]."""
+    import problems
+    rng = np.random.default_rng(seed)
+    Q = rng.random((n, n))
+    Pd = np.diag(Q.T @ Q).copy()
+    pv = rng.standard_normal(n)
+    A = rng.random((m, n))
+    b = A @ np.maximum(0.0, rng.standard_normal(n))
+    z = problems._z
+    P = problems.DenseNLP(
+        "qp_equality", n, m, 0, 0, np.zeros(0, np.int32),
+        f=lambda x: float(0.5 * x @ (Pd * x) + pv @ x), grad=lambda x: Pd * x + pv, hess=lambda x: np.diag(Pd),
+        g=lambda x: A @ x - b, jac_g=lambda x: A, hess_gy=lambda x, y: z(n, n),
+        h=lambda x: z(0), jac_h=lambda x: z(0, n), hess_hz=lambda x, zz: z(n, n), x0=rng.standard_normal(n))
+    return P, Pd, pv, A, b
+
+
+@pytest.mark.parametrize("backend", backends.BACKENDS)
+def test_qp_equality_sensitivities(backend):
+    """test/solver/qp_equality.jl:84-122: at the solution the sensitivities of x agree (1e-2, the reference's tolerance)
+    with the closed form -[P A'; A 0]^-1 [d(Px+p)/dtheta + d(A'y)/dtheta; d(Ax-b)/dtheta] and with -J^-1 dR/dtheta."""
+    from calipso_b200.solver import Solver, differentiate, initialize, residual_jacobian_parameters, solve
+    from oracle import oracle as orc
+    P, Pd, pv, A, b = equality_qp()
+    n, m = P.n, P.m
+    s = Solver(P, P.callback, binding=backends.binding(backend))
+    initialize(s, P.x0)
+    assert solve(s) is True
+    x, y = s.solution[:n], s.solution[s.kkt.iy]
+    assert np.abs(A @ x - b).max() < 1e-4                                   # qp_equality.jl:59-66
+    nth = n + n + m * n + m
+    Pxp = np.zeros((n, nth)); ATy = np.zeros((n, nth)); Axb = np.zeros((m, nth))
+    Pxp[:, :n] = np.diag(x)                                                 # d(P x + p)/d diag(P)
+    Pxp[:, n:2 * n] = np.eye(n)                                             # ... / dp
+    for j in range(n):
+        for i in range(m):
+            col = 2 * n + i + j * m                                         # vec(A), column-major
+            ATy[j, col] = y[i]                                              # d(A'y)_j / dA_ij
+            Axb[i, col] = x[j]                                              # d(Ax - b)_i / dA_ij
+    Axb[:, 2 * n + m * n:] = -np.eye(m)
+    H = residual_jacobian_parameters(n, m, 0, Pxp, ATy, None, Axb, None)
+    S = differentiate(s, H)
+    assert S.shape == (s.total, nth)
+    rz = np.block([[np.diag(Pd), A.T], [A, np.zeros((m, m))]])
+    closed = -np.linalg.solve(rz, np.vstack([Pxp + ATy, Axb]))
+    assert np.abs(closed[:n] - S[:n]).max() < 1e-2                          # qp_equality.jl:121
+    o = orc.Oracle(P.n, P.m, P.p, P.num_nonnegative, P.soc_dims, P.W_colptr, P.W_rowval, P.G_colptr, P.G_rowval,
+                   P.C_colptr, P.C_rowval, perm=s.kkt.symbolic()[0])
+    o.set_callback(P.callback)
+    o.use_superlu_fallback()
+    o.initialize(P.x0)
+    assert o.solve() == 1 and o.stats["total_iterations"] == s.iterations
+    So = o.differentiate(H)
+    assert np.abs(S - So).max() <= 1e-6 * max(1.0, np.abs(So).max())
+    o.residual_jacobian_variables()
+    full = -np.linalg.solve(o.dense_jacobian(), H)
+    assert np.abs(full[:n] - S[:n]).max() < 1e-2                            # qp_equality.jl:120,122

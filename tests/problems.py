@@ -190,6 +190,24 @@ def random_qp(seed=0, n=10, m=5, p=5) -> DenseNLP:
         h=lambda z: hv - Gm @ z, jac_h=lambda z: -Gm, hess_hz=lambda z, y: _z(n, n), x0=rng.standard_normal(n))
 
 
+def qp_nonnegative(seed=0, n=10, m=5) -> DenseNLP:
+    """test/solver/qp_nonnegative.jl:1-62: 1/2 x'P x + p'x with P diagonal, A x = b, x >= 0 (seeded draws)."""
+    rng = np.random.default_rng(seed)
+    xh = np.maximum(0.0, rng.standard_normal(n))
+    Q = rng.random((n, n))
+    Pd = np.diag(Q.T @ Q).copy()
+    pv = rng.standard_normal(n)
+    A = rng.random((m, n))
+    b = A @ xh
+    P = DenseNLP(
+        "qp_nonnegative", n, m, n, n, np.zeros(0, np.int32),
+        f=lambda x: float(0.5 * x @ (Pd * x) + pv @ x), grad=lambda x: Pd * x + pv, hess=lambda x: np.diag(Pd),
+        g=lambda x: A @ x - b, jac_g=lambda x: A, hess_gy=lambda x, y: _z(n, n),
+        h=lambda x: x.copy(), jac_h=lambda x: np.eye(n), hess_hz=lambda x, z: _z(n, n), x0=rng.standard_normal(n))
+    P.A, P.b = A, b
+    return P
+
+
 def test1() -> DenseNLP:
     """test/solver/test1.jl:1-35: 50 variables, 30 quadratic equalities, 3 inequalities."""
     n = 50

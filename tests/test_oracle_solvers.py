@@ -90,6 +90,18 @@ def test_portfolio():
     assert np.abs(P.b - P.A @ o.solution[:P.n] - s).max() < 1e-4
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_qp_nonnegative(seed):
+    """test/solver/qp_nonnegative.jl:49-62: stopping criteria, x >= -1e-4, ||A x - b||_inf < equality tolerance."""
+    P = problems.qp_nonnegative(seed)
+    o, rc = solve(P)
+    assert rc == 1
+    check_criteria(o)
+    x = o.solution[:P.n]
+    assert np.all(x > -1.0e-4)
+    assert np.abs(P.A @ x - P.b).max() < 1e-4
+
+
 @pytest.mark.parametrize("overwrite", [False, True])
 def test_pendulum_readme_quickstart(overwrite):
     """README.md:129-176 / test/examples/pendulum.jl:64-73 (BASELINE cfg1): converges, dynamics feasible, goal reached --

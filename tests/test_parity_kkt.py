@@ -195,7 +195,7 @@ def test_batch_of_instances_is_independent(backend):
 
 @pytest.mark.parametrize("backend", backends.BACKENDS)
 @pytest.mark.parametrize("name", ["wachter", "maratos", "knitro", "test1", "test2", "test3", "test4", "portfolio", "pendulum",
-                                  "pendulum_overwrite"])
+                                  "pendulum_overwrite", "qp_nonnegative"])
 def test_reference_solver_cases_through_host_callbacks(backend, name):
     """test/solver/*.jl cases through Solver / initialize! / solve! with host callbacks and the GPU hot path:
     same stopping criteria (e.g. wachter.jl:36-45) and the oracle's solution."""

@@ -359,3 +359,57 @@ def pendulum_overwrite() -> DenseNLP:
     P = pendulum(overwrite=True)
     P.name = "pendulum_overwrite"
     return P
+
+
+def rocket_landing(seed: int = 0, horizon: int = 101):
+    """test/examples/rocket_landing.jl:1-92 as a flat LQ-conic problem (every callback of this example is affine or
+    quadratic): states (position, velocity) in R^6, thrust in R^3, implicit-midpoint dynamics of
+    [v; (0, 0, -9.81) + f / mass] with h = 0.05 (:12-30), x_1 = (3, 2, 1, 0, 0, 0), x_T = 0 (:35-36, 45-49), cost
+    |p|^2 + 0.1 |v|^2 + 0.1 |u|^2 per stage (:39-42), thrust cone (u_3; u_1; u_2) in SOC(3) at every stage (:51-62).
+    Variables [x_1, u_1, ..., x_T] (trajectory_optimization/dynamics.jl:333-340), equalities ordered dynamics then
+    stage constraints (data.jl:51-55).  The action guess 1e-3 randn (:69) is seeded."""
+    import scipy.sparse as sp
+    from calipso_b200.lqc import ConicProblem, _csc
+    T, nx, nu, h, grav = horizon, 6, 3, 0.05, -9.81
+    nz = nx + nu
+    n = T * nx + (T - 1) * nu
+    m = (T - 1) * nx + 2 * nx
+    p = 3 * (T - 1)
+    x_init, x_goal = np.array([3.0, 2.0, 1.0, 0.0, 0.0, 0.0]), np.zeros(6)
+    G = sp.lil_matrix((m, n))
+    g0 = np.zeros(m)
+    I3 = np.eye(3)
+    for t in range(T - 1):
+        r, cx, cu, cy = t * nx, t * nz, t * nz + nx, (t + 1) * nz
+        # y_p - x_p - h/2 (x_v + y_v)
+        G[r:r + 3, cy:cy + 3] = I3; G[r:r + 3, cx:cx + 3] = -I3
+        G[r:r + 3, cx + 3:cx + 6] = -0.5 * h * I3; G[r:r + 3, cy + 3:cy + 6] = -0.5 * h * I3
+        # y_v - x_v - h ((0, 0, g) + u)
+        G[r + 3:r + 6, cy + 3:cy + 6] = I3; G[r + 3:r + 6, cx + 3:cx + 6] = -I3
+        G[r + 3:r + 6, cu:cu + 3] = -h * I3
+        g0[r + 5] = -h * grav
+    r = (T - 1) * nx
+    G[r:r + 6, 0:6] = np.eye(6); g0[r:r + 6] = -x_init
+    G[r + 6:r + 12, (T - 1) * nz:(T - 1) * nz + 6] = np.eye(6); g0[r + 6:r + 12] = -x_goal
+    qd = np.zeros(n)
+    for t in range(T):
+        qd[t * nz:t * nz + 6] = 2.0 * np.array([1.0, 1.0, 1.0, 0.1, 0.1, 0.1])
+        if t < T - 1:
+            qd[t * nz + 6:t * nz + 9] = 0.2
+    C = sp.lil_matrix((p, n))
+    for t in range(T - 1):
+        cu = t * nz + nx
+        C[3 * t, cu + 2] = 1.0; C[3 * t + 1, cu] = 1.0; C[3 * t + 2, cu + 1] = 1.0
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros(n)
+    for t in range(T):
+        x0[t * nz:t * nz + 6] = x_init + (x_goal - x_init) * t / (T - 1)      # linear_interpolation, utilities.jl:10
+    for t in range(T - 1):
+        x0[t * nz + 6:t * nz + 9] = 1.0e-3 * rng.standard_normal(3)
+    Wp, Wi, Wv = _csc(sp.diags(qd).tocsc())
+    Gp, Gi, Gv = _csc(G.tocsc())
+    Cp, Ci, Cv = _csc(C.tocsc())
+    return ConicProblem(n=n, m=m, p=p, num_nonnegative=0, soc_dims=np.full(T - 1, 3, dtype=np.int32),
+                        W_colptr=Wp, W_rowval=Wi, G_colptr=Gp, G_rowval=Gi, C_colptr=Cp, C_rowval=Ci,
+                        W_val=Wv, G_val=Gv, C_val=Cv, q=np.zeros(n), g0=g0, h0=np.zeros(p), x0=x0,
+                        meta=dict(family="rocket_landing", T=T, n_x=nx, n_u=nu, n_soc=T - 1, seed=seed))

@@ -115,6 +115,20 @@ def test_pendulum_readme_quickstart(overwrite):
     assert np.abs(x[P.ix[-1]:P.ix[-1] + 2] - P.x_goal).max() < 1e-4
 
 
+def test_rocket_landing_example():
+    """test/examples/rocket_landing.jl:72-91: converges, every thrust strictly inside its cone, stopping criteria."""
+    P = problems.rocket_landing()
+    o = orc.from_problem(P)
+    o.use_superlu_fallback()
+    o.initialize(P.x0)
+    assert o.solve() == 1
+    check_criteria(o)
+    x = o.solution[:P.n]
+    u = np.array([x[t * 9 + 6:t * 9 + 9] for t in range(P.meta["T"] - 1)])
+    assert np.all(np.linalg.norm(u[:, :2], axis=1) < u[:, 2])               # rocket_landing.jl:80
+    assert np.abs(x[-6:]).max() < 1e-4 and np.abs(x[:6] - [3.0, 2.0, 1.0, 0.0, 0.0, 0.0]).max() < 1e-4
+
+
 def test_lqc_family_converges_and_is_feasible():
     for P in (lqc.tiny(), lqc.cfg2()):
         o = orc.from_problem(P)

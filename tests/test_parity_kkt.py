@@ -142,9 +142,10 @@ def test_inertia_correction_schedule_matches_oracle(backend):
 
 
 @pytest.mark.parametrize("backend", backends.BACKENDS)
-@pytest.mark.parametrize("make", [lqc.tiny, lqc.cfg2, lqc.cfg2_hard])
+@pytest.mark.parametrize("make", [lqc.tiny, lqc.cfg2, lqc.cfg2_hard, problems.rocket_landing])
 def test_lq_solve_on_device_matches_oracle(backend, make):
-    """Whole solve! on the device (LQ callbacks) vs the oracle's solve!: same iteration counts, same solution."""
+    """Whole solve! on the device (LQ callbacks) vs the oracle's solve!: same iteration counts, same solution.
+    (rocket_landing: the reference's own example test/examples/rocket_landing.jl, an LQ-conic problem.)"""
     P = make()
     k = BatchKKT(P, binding=backends.binding(backend))
     perm, _, _ = k.symbolic()

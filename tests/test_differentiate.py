@@ -128,3 +128,95 @@ def test_qp_equality_sensitivities(backend):
     o.residual_jacobian_variables()
     full = -np.linalg.solve(o.dense_jacobian(), H)
     assert np.abs(full[:n] - S[:n]).max() < 1e-2                            # qp_equality.jl:120,122
+
+
+def double_integrator(seed=0, T=5):
+    """test/examples/double_integrator.jl:1-75 as a flat NLP: x_{t+1} = A x_t + B u_t, x_1 and x_T pinned, quadratic
+    stage costs; theta = per-stage [vec A; B; diag Q; R (; x_init)] and terminal [diag QT; x_goal] (:24-32)."""
+    import problems
+    A = np.array([[1.0, 1.0], [0.0, 1.0]]); Bv = np.array([0.0, 1.0])
+    Qd, R, QTd = np.array([1.0, 1.0]), 0.1, np.array([10.0, 10.0])
+    x_init, x_goal = np.array([0.0, 0.0]), np.array([1.0, 0.0])
+    nx, nu = 2, 1
+    n, m = T * nx + (T - 1) * nu, (T - 1) * nx + 2 * nx
+    ix = [t * 3 for t in range(T)]
+    iu = [t * 3 + 2 for t in range(T - 1)]
+    Gm = np.zeros((m, n)); g0 = np.zeros(m)
+    for t in range(T - 1):
+        r = 2 * t
+        Gm[r:r + 2, ix[t + 1]:ix[t + 1] + 2] = np.eye(2)
+        Gm[r:r + 2, ix[t]:ix[t] + 2] = -A
+        Gm[r:r + 2, iu[t]] = -Bv
+    r = 2 * (T - 1)
+    Gm[r:r + 2, ix[0]:ix[0] + 2] = np.eye(2); g0[r:r + 2] = -x_init
+    Gm[r + 2:r + 4, ix[T - 1]:ix[T - 1] + 2] = np.eye(2); g0[r + 2:r + 4] = -x_goal
+    wd = np.zeros(n)
+    for t in range(T - 1):
+        wd[ix[t]:ix[t] + 2] = Qd
+        wd[iu[t]] = R
+    wd[ix[T - 1]:ix[T - 1] + 2] = QTd
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros(n)
+    for t in range(T):
+        x0[ix[t]:ix[t] + 2] = x_init + (x_goal - x_init) * t / (T - 1)
+    for t in range(T - 1):
+        x0[iu[t]] = rng.standard_normal()
+    z = problems._z
+    P = problems.DenseNLP(
+        "double_integrator", n, m, 0, 0, np.zeros(0, np.int32),
+        f=lambda v: float(0.5 * v @ (wd * v)), grad=lambda v: wd * v, hess=lambda v: np.diag(wd),
+        g=lambda v: Gm @ v + g0, jac_g=lambda v: Gm, hess_gy=lambda v, y: z(n, n),
+        h=lambda v: z(0), jac_h=lambda v: z(0, n), hess_hz=lambda v, zz: z(n, n), x0=x0)
+    return P, Gm, wd, ix, iu
+
+
+@pytest.mark.parametrize("backend", ["emul"])     # (device code compiled for the host; the CUDA run of this case is still to do)
+def test_double_integrator_sensitivities(backend):
+    """test/examples/double_integrator.jl:64-165: solve with the example's tight tolerances, then the sensitivities of the
+    primal variables agree with -L_zz^-1 L_z,theta (z = [x; y]) to 1e-3 (:164)."""
+    from calipso_b200.solver import Options, Solver, differentiate, initialize, residual_jacobian_parameters, solve
+    T = 5
+    P, Gm, wd, ix, iu = double_integrator(0, T)
+    n, m = P.n, P.m
+    opt = Options(residual_tolerance=1.0e-12, equality_tolerance=1.0e-8, complementarity_tolerance=1.0e-8)
+    s = Solver(P, P.callback, options=opt, binding=backends.binding(backend))
+    initialize(s, P.x0)
+    assert solve(s) is True
+    v, y = s.solution[:n], s.solution[s.kkt.iy]
+    R_ = s.residual
+    assert max(np.abs(R_[:n]).max(), 0.0) < opt.optimality_tolerance               # :89-94
+    assert np.abs(R_[s.kkt.iy]).max() < opt.slack_tolerance                          # :96-100
+    assert np.abs(Gm @ v + P.g(np.zeros(n))).max() <= opt.equality_tolerance         # :102
+    sizes = [11] + [9] * (T - 2) + [4]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    nth = int(off[-1])
+    Oxp = np.zeros((n, nth)); Exp = np.zeros((n, nth)); Ep = np.zeros((m, nth))
+    for t in range(T - 1):
+        o_, lam = off[t], y[2 * t:2 * t + 2]
+        Oxp[ix[t], o_ + 6] = v[ix[t]]; Oxp[ix[t] + 1, o_ + 7] = v[ix[t] + 1]       # d(Q x)/d diag Q
+        Oxp[iu[t], o_ + 8] = v[iu[t]]                                               # d(R u)/dR
+        for j in range(2):
+            for i in range(2):
+                Exp[ix[t] + j, o_ + i + 2 * j] = -lam[i]                            # d(-A'lambda)_j / dA_ij
+                Ep[2 * t + i, o_ + i + 2 * j] = -v[ix[t] + j]                       # d(y - A x - B u)_i / dA_ij
+        for i in range(2):
+            Exp[iu[t], o_ + 4 + i] = -lam[i]                                        # d(-B'lambda) / dB_i
+            Ep[2 * t + i, o_ + 4 + i] = -v[iu[t]]
+    Ep[2 * (T - 1):2 * (T - 1) + 2, off[0] + 9:off[0] + 11] = -np.eye(2)            # x_1 - x_init
+    oT = off[T - 1]
+    Oxp[ix[T - 1], oT] = v[ix[T - 1]]; Oxp[ix[T - 1] + 1, oT + 1] = v[ix[T - 1] + 1]
+    Ep[2 * (T - 1) + 2:2 * (T - 1) + 4, oT + 2:oT + 4] = -np.eye(2)                 # x_T - x_goal
+    H = residual_jacobian_parameters(n, m, 0, Oxp, Exp, None, Ep, None)
+    S = differentiate(s, H)
+    Lzz = np.block([[np.diag(wd), Gm.T], [Gm, np.zeros((m, m))]])
+    closed = -np.linalg.solve(Lzz, np.vstack([Oxp + Exp, Ep]))
+    assert np.abs(closed[:n] - S[:n]).max() < 1.0e-3                                 # :164
+    # finite-difference spot check of the closed form itself: perturb x_goal[0]
+    col = oT + 2
+    d = 1e-6
+    g_shift = np.zeros(m); g_shift[2 * (T - 1) + 2] = -d
+    KKT = Lzz
+    rhs0 = -np.concatenate([np.zeros(n), P.g(np.zeros(n))])
+    z0 = np.linalg.solve(KKT, rhs0)
+    z1 = np.linalg.solve(KKT, rhs0 - np.concatenate([np.zeros(n), g_shift]))
+    assert np.abs((z1 - z0)[:n] / d - closed[:n, col]).max() < 1e-5

@@ -24,7 +24,15 @@ import backends  # noqa: E402
 from calipso_b200.solver import BatchKKT  # noqa: E402
 
 STEP_CASES = [("tiny", 0, 0), ("tiny", 0, 4), ("tiny", 1, 7), ("tiny", 2, 2)]
-SOLVE_CASES = [("tiny", 0), ("tiny", 3), ("cfg2", 0)]
+SOLVE_CASES = [("tiny", 0), ("tiny", 3), ("cfg2", 0), ("rocket", 0)]
+
+
+def instance(name, seed):
+    """LQ-conic instance by fixture name: the seeded LQC family, or the reference's rocket-landing example."""
+    if name == "rocket":
+        import problems
+        return problems.rocket_landing(seed)
+    return getattr(lqc, name)(seed)
 
 
 def product_perm(P):
@@ -59,7 +67,7 @@ def main():
         out.update(k_s=o.stats["k_s"], k_t=o.stats["k_t"], candidate=o.candidate.copy())
         np.savez_compressed(os.path.join(HERE, f"step_{name}_{seed}_{iters}.npz"), **state, **out)
     for name, seed in SOLVE_CASES:
-        P = getattr(lqc, name)(seed)
+        P = instance(name, seed)
         perm = product_perm(P)
         o = orc.from_problem(P, perm=perm)
         o.use_superlu_fallback()

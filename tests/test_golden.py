@@ -26,6 +26,13 @@ def parse(path):
     return parts[1], [int(x) for x in parts[2:]]
 
 
+def instance(name, seed):
+    if name == "rocket":                      # test/examples/rocket_landing.jl as an LQ-conic instance
+        import problems
+        return problems.rocket_landing(seed)
+    return getattr(lqc, name)(seed)
+
+
 def test_fixtures_are_committed():
     assert len(STEPS) >= 4 and len(SOLVES) >= 3
 
@@ -71,7 +78,7 @@ def test_newton_step_matches_golden(backend, path):
 def test_solve_matches_golden(backend, path):
     name, (seed,) = parse(path)
     g = np.load(path)
-    P = getattr(lqc, name)(seed)
+    P = instance(name, seed)
     k = BatchKKT(P, perm=g["perm"], binding=backends.binding(backend))
     k.load_lq(P)
     k.initialize(P.x0)

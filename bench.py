@@ -315,10 +315,14 @@ def run_gpu(args):
     ms_solve = (timed(lambda: k.kkt_factor_solve(5), 5) - ms_fact) / 5  # one reduced solve (+ rhs / recovery)
     b_unit = 12 * info["nnzK"] + 36 * info["nnzL"] + 40 * info["N"]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "of fallback: 6.65 TB/s (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        try:
+            measured = float(json.load(open(peaks_path)).get("hbm_gbs") or 0.0)
+        except (ValueError, TypeError, OSError):
+            measured = 0.0
+        if measured > 0.0:
+            peak, peak_src = measured, "of measured: MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"
     kkt_achieved = b_unit * B / (ms_kkt * 1e-3) / 1e9
     tpath2 = os.path.join(ROOT, "profiles", "lq_step_traffic.json")
     # measured DRAM bytes of one Newton iteration of one instance (ncu capture of a launch in which every instance ran

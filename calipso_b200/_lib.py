@@ -32,7 +32,7 @@ S = {name: i for i, name in enumerate(SCALARS)}
 S_COUNT = 24
 STATS = ["inertia_pos", "inertia_neg", "inertia_zero", "n_trials", "n_refine", "refine_ok", "k_s", "k_t", "status",
          "used_fallback", "fallbacks", "total_iterations", "outer", "line_search", "converged", "gmres_iters",
-         "filter_index", "inner", "factorizations", "solves"]
+         "filter_index", "inner", "factorizations", "solves", "unrefined_steps"]
 I = {name: i for i, name in enumerate(STATS)}
 I_COUNT = 24
 STATUS_TEXT = {0: "ok", 1: "inertia correction failure", 2: "iterative refinement failure", 3: "cone search failure",
@@ -41,8 +41,9 @@ STATUS_TEXT = {0: "ok", 1: "inertia correction failure", 2: "iterative refinemen
 PROFILE = ["assemble", "factor_leaves", "factor_small", "factor_big_stage", "factor_big_gemm", "factor_big_panel",
            "factor_big_generic", "solve_fwd", "solve_bwd", "rhs_recover", "jtimes", "eval_linesearch", "cone_residual",
            "inertia", "total", "sf_bulk", "sf_pull", "sf_sweep", "sf_push", "sf_other", "sb_gather", "sb_sweep", "sb_other",
-           "sb_leaves"]
-PROF_COUNT = 24
+           "sb_leaves", "chain_fwd_tma", "chain_fwd_sweep", "chain_fwd_wait", "chain_bwd_tma", "chain_bwd_wait",
+           "chain_bwd_sweep", "spare0", "spare1"]
+PROF_COUNT = 32
 
 EV_OBJECTIVE, EV_GRADIENT, EV_EQUALITY, EV_CONE, EV_EQUALITY_DUAL_GRAD, EV_CONE_DUAL_GRAD = 1, 2, 4, 8, 16, 32
 EV_HESSIAN, EV_EQUALITY_JAC, EV_CONE_JAC = 64, 128, 256

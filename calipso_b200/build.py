@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcalipso_b200.so")
 SOURCES = ["api.cu", "symbolic.cpp"]
-HEADERS = ["device_core.h", "device_newton.h", "symbolic.h", os.path.join("..", "..", "include", "calipso_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".h")) + [os.path.join("..", "..", "include", "calipso_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--extended-lambda"]
 

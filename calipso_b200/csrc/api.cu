@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -653,12 +654,17 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
         CUDA_OK(cudaGetLastError());                                          \
     } while (0)
 // kernels that factor or solve get the CTA work area (panel + Y staging) as dynamic shared memory
+// (the opt-in is a per-device function attribute: remembered per device, atomically -- handles on several GPUs and
+// several host threads may share one process)
+#define CB_MAX_DEVICES 64
 #define LAUNCH_SMEM_T(kernel, T, ...)                                                                     \
     do {                                                                                                  \
-        static size_t configured = 0;                                                                     \
-        if (h->smem_bytes > configured) {                                                                 \
+        static std::atomic<size_t> configured[CB_MAX_DEVICES];                                            \
+        const int dv_ = h->device < CB_MAX_DEVICES ? h->device : CB_MAX_DEVICES - 1;                      \
+        if (h->device >= CB_MAX_DEVICES - 1 || h->smem_bytes > configured[dv_].load()) {                  \
             CUDA_OK(cudaFuncSetAttribute(kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
-            configured = h->smem_bytes;                                                                   \
+            size_t cur_ = configured[dv_].load();                                                         \
+            while (cur_ < h->smem_bytes && !configured[dv_].compare_exchange_weak(cur_, h->smem_bytes)) {} \
         }                                                                                                 \
         kernel<T><<<h->batch, T, h->smem_bytes, h->stream>>>(__VA_ARGS__);                                \
     } while (0)

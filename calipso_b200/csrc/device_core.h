@@ -117,7 +117,10 @@ enum {
     PROF_EVAL_LINESEARCH, PROF_CONE_RESIDUAL, PROF_INERTIA, PROF_TOTAL,
     // sub-phases of the shared-memory solve
     PROF_SF_BULK, PROF_SF_PULL, PROF_SF_SWEEP, PROF_SF_PUSH, PROF_SF_OTHER, PROF_SB_GATHER, PROF_SB_SWEEP, PROF_SB_OTHER,
-    PROF_SB_LEAVES, PROF_COUNT = 24
+    PROF_SB_LEAVES,
+    // chain runs of the shared-memory solve, as seen by the sweep warp (forward / backward): waiting for a TMA part, sweeping,
+    // waiting for the other warps
+    PROF_CF_TMA, PROF_CF_SWEEP, PROF_CF_WAIT, PROF_CB_TMA, PROF_CB_WAIT, PROF_CB_SWEEP, PROF_SPARE0, PROF_SPARE1, PROF_COUNT = 32
 };
 
 // per-instance scalar slots
@@ -130,7 +133,7 @@ enum {
 enum {
     I_INERTIA_POS = 0, I_INERTIA_NEG, I_INERTIA_ZERO, I_TRIALS, I_REFINE, I_REFINE_OK, I_KS, I_KT, I_STATUS,
     I_USED_FALLBACK, I_FALLBACKS, I_TOTAL_ITERATIONS, I_OUTER, I_LINE_SEARCH, I_CONVERGED, I_GMRES_ITERS,
-    I_FILTER_INDEX, I_INNER, I_FACTORIZATIONS, I_SOLVES, I_COUNT = 24
+    I_FILTER_INDEX, I_INNER, I_FACTORIZATIONS, I_SOLVES, I_UNREFINED_STEPS, I_COUNT = 24
 };
 // status codes (also the C ABI's, include/calipso_b200.h)
 enum { ST_OK = 0, ST_INERTIA_FAILURE = 1, ST_REFINEMENT_FAILURE = 2, ST_CONE_SEARCH_FAILURE = 3, ST_ZERO_PIVOT = 4 };
@@ -1056,12 +1059,27 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
             pt.stop(PROF_FACTOR_LEAVES);
         });
     pt.stop(PROF_FACTOR_SMALL);
-    double pos = scope_sum(ctx, P.N, [&](int i) { return D[i] > 0.0 ? 1.0 : 0.0; });
-    double zer = scope_sum(ctx, P.N, [&](int i) { return D[i] == 0.0 ? 1.0 : 0.0; });
+    // one reduction for the three counts (exact in a double: N < 2^17): negatives are counted explicitly so that a NaN
+    // pivot is neither positive nor negative and fails the inertia test, as in the reference (linear_solver.jl:33-44)
+    long long c;
+    if (P.N < 131072) {
+        c = (long long)scope_sum(ctx, P.N, [&](int i) {
+            const double d = D[i];
+            return (d > 0.0 ? 1.0 : 0.0) + (d <= 0.0 ? 131072.0 : 0.0) + (d == 0.0 ? 17179869184.0 : 0.0);
+        });
+    } else {
+        const long long cp = (long long)scope_sum(ctx, P.N, [&](int i) { return D[i] > 0.0 ? 1.0 : 0.0; });
+        const long long cn = (long long)scope_sum(ctx, P.N, [&](int i) { return D[i] <= 0.0 ? 1.0 : 0.0; });
+        const long long cz = (long long)scope_sum(ctx, P.N, [&](int i) { return D[i] == 0.0 ? 1.0 : 0.0; });
+        c = -1;
+        if (ctx.tid == 0) { istat[I_INERTIA_POS] = (int)cp; istat[I_INERTIA_NEG] = (int)cn; istat[I_INERTIA_ZERO] = (int)cz; }
+    }
     if (ctx.tid == 0) {
-        istat[I_INERTIA_POS] = (int)pos;
-        istat[I_INERTIA_NEG] = P.N - (int)pos;
-        istat[I_INERTIA_ZERO] = (int)zer;
+        if (c >= 0) {
+            istat[I_INERTIA_POS] = (int)(c & 131071);
+            istat[I_INERTIA_NEG] = (int)((c >> 17) & 131071);
+            istat[I_INERTIA_ZERO] = (int)(c >> 34);
+        }
         istat[I_FACTORIZATIONS]++;
     }
     ctx.sync();
@@ -1070,13 +1088,341 @@ CB_DEVN void ldl_factor(const Ctx &ctx, const DevProblem &P, double *pan, double
 
 
 #if CB_ON_DEVICE
-// Fast path of ldl_solve (same arithmetic).  The permuted vector lives in shared memory for the whole solve; the chain
-// of shared-memory supernodes streams its factor panels, in one or two column parts, through two shared-memory
-// buffers filled by TMA bulk copies one part ahead (mbarrier complete_tx), so no global-memory latency sits on the
-// critical path of the elimination-tree chain.  Per chain supernode: the w x w unit-triangular block is solved by ONE
-// warp with register-resident unknowns and shuffles (no CTA barrier per pivot), the rectangular part L_R is a mat-vec
-// spread over the whole CTA (four threads per row / column, shuffle-reduced).  Singleton leaves are handled in bulk
-// by four-lane groups (coalesced).  Work area: x[N] | part buffer 0 | part buffer 1 | y[64].
+// ---- fast path of ldl_solve (same arithmetic): shared-memory solve with warp-specialised chain runs ---------------
+// The permuted vector lives in shared memory for the whole solve.  The shared-memory ("chain") supernodes stream their
+// factor panels, in one or two column parts, through two shared-memory slots filled by TMA bulk copies (mbarrier
+// complete_tx) up to two parts ahead.  A *chain run* (symbolic.cpp: consecutive CTA-scope phases on the shared-memory
+// path with no bulk pull in between; for a trajectory-optimisation KKT matrix: the whole stage chain) is processed
+// without CTA-wide barriers:
+//   * warp 0 runs the triangular sweeps, eight pivots at a time: the eight current values are broadcast with shuffles,
+//     every lane solves the 8x8 unit-triangular block redundantly in registers (no shuffle / FMA ping-pong per pivot) and
+//     then updates its own rows (forward) or columns (backward) -- the same FMA sequence per entry as a pivot-by-pivot
+//     sweep, so the results do not depend on the blocking;
+//   * the other warps apply the rectangular parts (forward: x[R] -= L_R y, backward: t = L_R' x[R] + the pivots solved
+//     before), four threads per row / column, and issue the TMA copies;
+//   * the two sides meet at named barriers (bar.arrive / bar.sync, producer-consumer): forward, the sweep of the next
+//     column part overlaps the rectangular update of the previous one.
+// Singleton leaves are handled in bulk by four-lane groups (coalesced); supernodes off the shared-memory path keep the
+// generic code.  Work area: x[N] | slot 0 | slot 1 | y[64] | zero cell | x[R] window.
+enum { CB_BAR_A0 = 1, CB_BAR_A1 = 2, CB_BAR_B0 = 3, CB_BAR_B1 = 4, CB_BAR_REST = 5 };   // named barriers (0 = __syncthreads)
+// (immediate barrier numbers: with a register operand ptxas reserves all 16 hardware barriers for the CTA)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    switch (id) {
+    case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+    case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+    case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+    case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+    default: asm volatile("bar.sync 5, %0;" ::"r"(nthreads) : "memory"); break;
+    }
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    switch (id) {
+    case 1: asm volatile("bar.arrive 1, %0;" ::"r"(nthreads) : "memory"); break;
+    case 2: asm volatile("bar.arrive 2, %0;" ::"r"(nthreads) : "memory"); break;
+    case 3: asm volatile("bar.arrive 3, %0;" ::"r"(nthreads) : "memory"); break;
+    default: asm volatile("bar.arrive 4, %0;" ::"r"(nthreads) : "memory"); break;
+    }
+}
+
+struct ChainTask { int s, c0, w, nR, rows_off, panel_off, h1; };
+__device__ __forceinline__ ChainTask chain_task(const DevProblem &P, int bi)
+{
+    int4 d0, d1;
+    if (bi < cb_chain_n) { d0 = cb_chain[2 * bi]; d1 = cb_chain[2 * bi + 1]; }       // cached: no global-memory chase
+    else { const int4 *g = reinterpret_cast<const int4 *>(P.bdesc) + 2 * bi; d0 = g[0]; d1 = g[1]; }
+    return ChainTask{d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
+}
+__device__ __forceinline__ Phase load_phase(const DevProblem &P, int pidx)
+{
+    Phase ph;
+    if (cb_phase_n > 0) {
+        const int *pp = cb_phase + 6 * pidx;
+        ph.mode = pp[0]; ph.begin = pp[1]; ph.end = pp[2]; ph.ebegin = pp[3]; ph.eend = pp[4]; ph.first_big = pp[5];
+    } else {
+        ph = P.phases[pidx];
+    }
+    return ph;
+}
+
+// The TMA part stream of one solve direction.  Every thread tracks the (uniform) counters; part g lands in slot
+// (base + g) & 1 and completes phase ((base + g) >> 1) & 1 of that slot's mbarrier.
+struct PartStream {
+    const double *pan;
+    const int *parts;       // (panel offset, doubles) pairs in issue order
+    int nparts, issued, done;
+    unsigned base;          // mbarrier uses before this direction started
+    int buf_off, buf_len;
+};
+__device__ __forceinline__ void part_issue(const PartStream &st, int g, int off, int doubles)      // ONE thread
+{
+    const unsigned u = st.base + (unsigned)g;
+    const unsigned bytes = (unsigned)doubles * 8u;
+    fence_proxy_async();
+    mbar_expect_tx(&cb_bars[u & 1], bytes);
+    tma_bulk_g2s(cb_dyn_smem + st.buf_off + (int)(u & 1) * st.buf_len, st.pan + off, bytes, &cb_bars[u & 1]);
+}
+__device__ __forceinline__ const double *part_wait(const PartStream &st, int g)      // returns the slot's base
+{
+    const unsigned u = st.base + (unsigned)g;
+    mbar_wait(&cb_bars[u & 1], (u >> 1) & 1);
+    return cb_dyn_smem + st.buf_off + (int)(u & 1) * st.buf_len;
+}
+// (all threads, after a CTA barrier) make sure the next two parts are in flight
+__device__ __forceinline__ void part_prefetch(PartStream &st, int leader)
+{
+    const int want = min(st.done + 2, st.nparts);
+    if ((int)threadIdx.x == leader)
+        for (int g = st.issued; g < want; g++) part_issue(st, g, st.parts[2 * g], st.parts[2 * g + 1]);
+    if (st.issued < want) st.issued = want;
+}
+
+// Forward sweep of columns [k0, k1) of a unit-lower-triangular pivot block (zeros stored on and above the diagonal):
+// lane holds the unknowns of rows lane (y0) and lane + 32 (y1); L + k * nrow is column k of the panel.  Four pivots per
+// step; every shared-memory load of a step is issued before the shuffles (the addresses do not depend on the data), so
+// the dependent chain of a step is one shuffle and four FMAs.  (Measured on B200, tools/microbench/sweep_blocked.cu: 28
+// cycles per pivot against 55 pivot by pivot; inside the solve kernel the single sweep warp is bound by its own
+// instruction issue, ~70 cycles per pivot either way.)
+__device__ __forceinline__ void sweep_forward_blocked(const double *__restrict__ L, int nrow, int k0, int k1, int lane,
+                                                      double &y0, double &y1)
+{
+    const int r0 = min(lane, nrow - 1), r1 = min(lane + 32, nrow - 1);
+    int kb = k0;
+    for (; kb + 4 <= k1; kb += 4) {
+        const double *c0 = L + kb * nrow, *c1 = c0 + nrow, *c2 = c1 + nrow, *c3 = c2 + nrow;
+        const double l10 = c0[kb + 1], l20 = c0[kb + 2], l30 = c0[kb + 3], l21 = c1[kb + 2], l31 = c1[kb + 3], l32 = c2[kb + 3];
+        const double a00 = c0[r0], a01 = c1[r0], a02 = c2[r0], a03 = c3[r0];
+        const double a10 = c0[r1], a11 = c1[r1], a12 = c2[r1], a13 = c3[r1];
+        const double v0 = __shfl_sync(0xffffffffu, kb < 32 ? y0 : y1, kb & 31);
+        double v1 = __shfl_sync(0xffffffffu, kb + 1 < 32 ? y0 : y1, (kb + 1) & 31);
+        double v2 = __shfl_sync(0xffffffffu, kb + 2 < 32 ? y0 : y1, (kb + 2) & 31);
+        double v3 = __shfl_sync(0xffffffffu, kb + 3 < 32 ? y0 : y1, (kb + 3) & 31);
+        v1 -= l10 * v0;
+        v2 -= l20 * v0;
+        v3 -= l30 * v0;
+        y0 -= a00 * v0;
+        y1 -= a10 * v0;
+        v2 -= l21 * v1;
+        v3 -= l31 * v1;
+        y0 -= a01 * v1;
+        y1 -= a11 * v1;
+        v3 -= l32 * v2;
+        y0 -= a02 * v2;
+        y1 -= a12 * v2;
+        y0 -= a03 * v3;
+        y1 -= a13 * v3;
+    }
+    for (; kb < k1; kb++) {                           // remainder: pivot by pivot
+        const double l0 = L[kb * nrow + r0], l1 = L[kb * nrow + r1];
+        const double yk = __shfl_sync(0xffffffffu, kb < 32 ? y0 : y1, kb & 31);
+        y0 -= l0 * yk;
+        y1 -= l1 * yk;
+    }
+}
+// Backward sweep (L' z = v) restricted to columns [k0, k1): lane holds columns lane (z0) and lane + 32 (z1); lanes whose
+// column is outside the part read a zero cell with stride 0.  Four pivots per step, from the last column down.
+__device__ __forceinline__ void sweep_backward_blocked(const double *__restrict__ L, int nrow, int k0, int k1, int lane,
+                                                       const double *zero_cell, double &z0, double &z1)
+{
+    const bool in0 = lane >= k0 && lane < k1, in1 = lane + 32 >= k0 && lane + 32 < k1;
+    const double *p0 = in0 ? L + lane * nrow : zero_cell, *p1 = in1 ? L + (lane + 32) * nrow : zero_cell;
+    const int s0 = in0 ? 1 : 0, s1 = in1 ? 1 : 0;
+    int kt = k1;
+    for (; kt - 4 >= k0; kt -= 4) {
+        const int kb = kt - 4;
+        // rows kb+1 .. kb+3 of the block (row r of column c at L[c * nrow + r])
+        const double *c0 = L + kb * nrow, *c1 = c0 + nrow, *c2 = c1 + nrow;
+        const double l10 = c0[kb + 1], l20 = c0[kb + 2], l30 = c0[kb + 3], l21 = c1[kb + 2], l31 = c1[kb + 3], l32 = c2[kb + 3];
+        const double a00 = p0[kb * s0], a01 = p0[(kb + 1) * s0], a02 = p0[(kb + 2) * s0], a03 = p0[(kb + 3) * s0];
+        const double a10 = p1[kb * s1], a11 = p1[(kb + 1) * s1], a12 = p1[(kb + 2) * s1], a13 = p1[(kb + 3) * s1];
+        double v0 = __shfl_sync(0xffffffffu, kb < 32 ? z0 : z1, kb & 31);
+        double v1 = __shfl_sync(0xffffffffu, kb + 1 < 32 ? z0 : z1, (kb + 1) & 31);
+        double v2 = __shfl_sync(0xffffffffu, kb + 2 < 32 ? z0 : z1, (kb + 2) & 31);
+        const double v3 = __shfl_sync(0xffffffffu, kb + 3 < 32 ? z0 : z1, (kb + 3) & 31);
+        v2 -= l32 * v3;
+        v1 -= l31 * v3;
+        v0 -= l30 * v3;
+        z0 -= a03 * v3;
+        z1 -= a13 * v3;
+        v1 -= l21 * v2;
+        v0 -= l20 * v2;
+        z0 -= a02 * v2;
+        z1 -= a12 * v2;
+        v0 -= l10 * v1;
+        z0 -= a01 * v1;
+        z1 -= a11 * v1;
+        z0 -= a00 * v0;
+        z1 -= a10 * v0;
+    }
+    for (int k = kt - 1; k > k0; k--) {               // remainder: pivot by pivot
+        const double l0 = p0[k * s0], l1 = p1[k * s1];
+        const double zk = __shfl_sync(0xffffffffu, k < 32 ? z0 : z1, k & 31);
+        z0 -= l0 * zk;
+        z1 -= l1 * zk;
+    }
+}
+
+// Forward substitution through the chain supernodes bi0 .. bi0 + ntasks - 1 (see the header comment).  Ends with a CTA barrier.
+__device__ __forceinline__ void chain_run_forward(const DevProblem &P, PartStream &st, int bi0, int ntasks, double *xs, double *yv,
+                                                  long long *prof)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int leader = 32;
+    part_prefetch(st, leader);
+    int g = st.done;
+    if (wid == 0) {
+        ProfTimer pc{prof, 0};
+        pc.start();
+        int prev_parts = 0;
+        for (int t = 0; t < ntasks; t++) {
+            const ChainTask d = chain_task(P, bi0 + t);
+            const int nrow = d.w + d.nR, np = d.h1 < d.w ? 2 : 1;
+            for (int q = prev_parts; q > 0; q--) named_bar_sync(CB_BAR_B0 + (int)((st.base + g - q) & 1), nthr);   // pushes into these pivots
+            pc.stop(PROF_CF_WAIT);
+            double y0 = lane < d.w ? xs[d.c0 + lane] : 0.0, y1 = lane + 32 < d.w ? xs[d.c0 + lane + 32] : 0.0;
+            for (int a = 0; a < np; a++, g++) {
+                const int k0 = a == 0 ? 0 : d.h1, k1 = (a == 0 && np == 2) ? d.h1 : d.w;
+                const double *L = part_wait(st, g) - k0 * nrow;
+                pc.stop(PROF_CF_TMA);
+                sweep_forward_blocked(L, nrow, k0, k1, lane, y0, y1);
+                if (lane >= k0 && lane < k1) { yv[lane] = y0; xs[d.c0 + lane] = y0; }
+                if (lane + 32 >= k0 && lane + 32 < k1) { yv[lane + 32] = y1; xs[d.c0 + lane + 32] = y1; }
+                named_bar_arrive(CB_BAR_A0 + (int)((st.base + g) & 1), nthr);      // y[k0 .. k1) published
+                pc.stop(PROF_CF_SWEEP);
+            }
+            prev_parts = np;
+        }
+        for (int q = prev_parts; q > 0; q--) named_bar_sync(CB_BAR_B0 + (int)((st.base + g - q) & 1), nthr);
+        pc.stop(PROF_CF_WAIT);
+    } else {
+        const int part = tid & 3, grp = (tid - 32) >> 2, ngrp = (nthr - 32) >> 2;
+        for (int t = 0; t < ntasks; t++) {
+            const ChainTask d = chain_task(P, bi0 + t);
+            const int nrow = d.w + d.nR, np = d.h1 < d.w ? 2 : 1, nR = d.nR, w = d.w;
+            const int *__restrict__ R = P.rows + d.rows_off;
+            const int rI = grp < nR ? R[grp] : 0;       // row index of this thread's first push row, in flight early
+            for (int a = 0; a < np; a++, g++) {
+                const int k0 = a == 0 ? 0 : d.h1, k1 = (a == 0 && np == 2) ? d.h1 : w;
+                int noff = 0, nlen = 0;
+                const bool refill = tid == leader && g + 2 < st.nparts;
+                if (refill) { noff = st.parts[2 * (g + 2)]; nlen = st.parts[2 * (g + 2) + 1]; }
+                const double *L = part_wait(st, g) - k0 * nrow;
+                named_bar_sync(CB_BAR_A0 + (int)((st.base + g) & 1), nthr);
+                for (int base = 0; base < nR; base += ngrp) {      // x[R] -= L_R[:, k0:k1) y[k0:k1), four threads per row
+                    const int i = base + grp;
+                    double a0 = 0.0, a1 = 0.0;
+                    if (i < nR) {
+                        const double *Lr = L + w + i + (k0 + part) * nrow;
+                        const double *yp = yv + k0 + part;
+                        const int cnt = (k1 - k0 - part + 3) >> 2;
+                        int j = 0;
+                        for (; j + 1 < cnt; j += 2) {
+                            a0 += Lr[0] * yp[0];
+                            a1 += Lr[4 * nrow] * yp[4];
+                            Lr += 8 * nrow;
+                            yp += 8;
+                        }
+                        if (j < cnt) a0 += Lr[0] * yp[0];
+                    }
+                    double acc = a0 + a1;
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    if (part == 0 && i < nR) xs[base == 0 ? rI : R[i]] -= acc;
+                }
+                named_bar_sync(CB_BAR_REST, nthr - 32);            // every reader of the slot is done
+                named_bar_arrive(CB_BAR_B0 + (int)((st.base + g) & 1), nthr);      // pushes of this part are in xs
+                if (refill) part_issue(st, g + 2, noff, nlen);      // (after the arrival: off the sweep warp's critical path)
+            }
+        }
+    }
+    st.done = g;
+    st.issued = max(st.issued, min(g + 2, st.nparts));
+    __syncthreads();
+}
+
+// Backward substitution through the chain supernodes bi0 + ntasks - 1 .. bi0 (in that order).  Ends with a CTA barrier.
+__device__ __forceinline__ void chain_run_backward(const DevProblem &P, PartStream &st, int bi0, int ntasks, double *xs, double *yv,
+                                                   double *xr, const double *zero_cell, long long *prof)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int leader = 32;
+    part_prefetch(st, leader);
+    const int g_first = st.done;
+    int g = g_first;
+    if (wid == 0) {
+        ProfTimer pc{prof, 0};
+        pc.start();
+        for (int t = ntasks - 1; t >= 0; t--) {
+            const ChainTask d = chain_task(P, bi0 + t);
+            const int nrow = d.w + d.nR, np = d.h1 < d.w ? 2 : 1;
+            double z0 = lane < d.w ? xs[d.c0 + lane] : 0.0, z1 = lane + 32 < d.w ? xs[d.c0 + lane + 32] : 0.0;
+            for (int a = np - 1; a >= 0; a--, g++) {
+                const int k0 = a == 0 ? 0 : d.h1, k1 = (a == 0 && np == 2) ? d.h1 : d.w;
+                const double *L = part_wait(st, g) - k0 * nrow;
+                pc.stop(PROF_CB_TMA);
+                named_bar_sync(CB_BAR_A0 + (int)((st.base + g) & 1), nthr);        // t[k0 .. k1) gathered
+                pc.stop(PROF_CB_WAIT);
+                if (lane >= k0 && lane < k1) z0 -= yv[lane];
+                if (lane + 32 >= k0 && lane + 32 < k1) z1 -= yv[lane + 32];
+                sweep_backward_blocked(L, nrow, k0, k1, lane, zero_cell, z0, z1);
+                if (lane >= k0 && lane < k1) xs[d.c0 + lane] = z0;
+                if (lane + 32 >= k0 && lane + 32 < k1) xs[d.c0 + lane + 32] = z1;
+                named_bar_arrive(CB_BAR_B0 + (int)((st.base + g) & 1), nthr);      // x[c0 + k0 .. c0 + k1) final
+                pc.stop(PROF_CB_SWEEP);
+            }
+        }
+    } else {
+        const int part = tid & 3, grp = (tid - 32) >> 2, ngrp = (nthr - 32) >> 2, nrest = nthr - 32;
+        for (int t = ntasks - 1; t >= 0; t--) {
+            const ChainTask d = chain_task(P, bi0 + t);
+            const int nrow = d.w + d.nR, np = d.h1 < d.w ? 2 : 1, nR = d.nR, w = d.w;
+            const int *__restrict__ R = P.rows + d.rows_off;
+            for (int a = np - 1; a >= 0; a--, g++) {
+                const int k0 = a == 0 ? 0 : d.h1, k1 = (a == 0 && np == 2) ? d.h1 : w;
+                if (g > g_first) {
+                    // the previous part's sweep is done: its unknowns are final and its slot is free for part g + 1
+                    int noff = 0, nlen = 0;
+                    const bool refill = tid == leader && g + 1 < st.nparts;
+                    if (refill) { noff = st.parts[2 * (g + 1)]; nlen = st.parts[2 * (g + 1) + 1]; }
+                    named_bar_sync(CB_BAR_B0 + (int)((st.base + g - 1) & 1), nthr);
+                    if (refill) part_issue(st, g + 1, noff, nlen);
+                }
+                if (a == np - 1) {          // x[R] (final), staged once for both parts
+                    for (int i = tid - 32; i < nR; i += nrest) xr[i] = xs[R[i]];
+                    named_bar_sync(CB_BAR_REST, nrest);
+                }
+                const double *L = part_wait(st, g) - k0 * nrow;
+                // t_k = sum_{r >= k1} L[r, k] x_r for the columns k of this part: rows k1 .. w-1 are the pivots of the part
+                // solved before (final in xs), rows w .. are R; four threads per column
+                for (int base = k0; base < k1; base += ngrp) {
+                    const int k = base + grp;
+                    double a0 = 0.0, a1 = 0.0;
+                    if (k < k1) {
+                        const double *Lc = L + k * nrow;
+                        const double *xp = xs + d.c0;
+                        int r = k1 + part;
+                        for (; r + 4 < w; r += 8) { a0 += Lc[r] * xp[r]; a1 += Lc[r + 4] * xp[r + 4]; }
+                        if (r < w) { a0 += Lc[r] * xp[r]; r += 4; }
+                        const double *xq = xr - w;
+                        for (; r + 4 < nrow; r += 8) { a0 += Lc[r] * xq[r]; a1 += Lc[r + 4] * xq[r + 4]; }
+                        if (r < nrow) a0 += Lc[r] * xq[r];
+                    }
+                    double acc = a0 + a1;
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    if (part == 0 && k < k1) yv[k] = acc;
+                }
+                named_bar_arrive(CB_BAR_A0 + (int)((st.base + g) & 1), nthr);
+            }
+        }
+        if (g > g_first) named_bar_sync(CB_BAR_B0 + (int)((st.base + g - 1) & 1), nthr);      // pairs the last sweep's arrival
+    }
+    st.done = g;
+    st.issued = max(st.issued, min(g + 1, st.nparts));
+    __syncthreads();
+}
+
 __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P, const double *__restrict__ pan,
                                             const double *D, const double *__restrict__ Dinv,
                                             const double *__restrict__ Lcsr, const double *b, double *x,
@@ -1086,43 +1432,20 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     pt.start();
     ps.start();
     const int N = P.N, Npad = (N + 1) & ~1;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, wid = tid >> 5, nw = nthr >> 5;
     double *xs = cb_dyn_smem;
-    const int buf_off = Npad, buf_len = P.max_sb_doubles;      // part buffer `slot` at cb_dyn_smem + buf_off + slot * buf_len
+    const int buf_off = Npad, buf_len = P.max_sb_doubles;      // slot s at cb_dyn_smem + buf_off + s * buf_len
     double *yv = cb_dyn_smem + buf_off + 2 * buf_len;            // (named from cb_dyn_smem so that accesses stay LDS/STS)
     double *zero_cell = yv + 64;
     double *xr = yv + 80;                                         // x[R] of the current chain supernode (backward)
-    unsigned long long *bars = cb_bars;
+    const int leader = 32;
     if (tid == 0) *zero_cell = 0.0;
     for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
-    // the barriers live for the whole kernel: continue the issue/consume numbering where the previous solve stopped
-    unsigned issued = cb_bar_uses, consumed = issued;
-    const int *parts = P.parts_fwd;
-    int nparts = P.nparts_fwd, next_part = 0;
-    auto issue = [&]() {    // called by all threads after a CTA barrier that freed the slot; the first lane of the LAST warp
-                            // launches the copy (warp 0 runs the triangular sweeps: keep the proxy fence off its path)
-        if (next_part < nparts) {
-            if (tid == nthr - 32) {
-                const int off = parts[2 * next_part];
-                const unsigned bytes = (unsigned)parts[2 * next_part + 1] * 8u;
-                const int slot = issued & 1;
-                fence_proxy_async();
-                mbar_expect_tx(&bars[slot], bytes);
-                tma_bulk_g2s(cb_dyn_smem + buf_off + slot * buf_len, pan + off, bytes, &bars[slot]);
-            }
-            issued++;
-            next_part++;
-        }
-    };
-    auto acquire = [&]() -> int {       // returns the slot that holds the part
-        const int slot = consumed & 1;
-        mbar_wait(&bars[slot], (unsigned)((consumed >> 1) & 1));
-        consumed++;
-        return slot;
-    };
+    // the mbarriers live for the whole kernel: continue the use numbering where the previous solve stopped
+    PartStream st{pan, P.parts_fwd, P.nparts_fwd, 0, 0, cb_bar_uses, buf_off, buf_len};
     __syncthreads();
     ps.stop(PROF_SF_PULL);                                        // (counter: permutation gather)
-    issue();
+    part_prefetch(st, leader);
     // bulk pass: every column pulls the contributions of its singleton-leaf descendants (x_leaf = b_leaf is final);
     // four lanes per column, columns without leaf descendants are not visited
     {
@@ -1157,105 +1480,58 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
     }
     __syncthreads();
     ps.stop(PROF_SF_BULK);
-    for_each_supernode(
-        ctx, P, true,
-        [&](const Ctx &c, int s, int hint) {
-            const Ctx &ctx = c;
-            const int bi = c.warp_scope ? -1 : (hint != -2 ? hint : P.big_index[s]);
-            int c0, w, nR, rows_off, h1 = 0;
-            if (bi >= 0 && bi < cb_chain_n) {        // descriptor from shared memory: no global-memory chase
-                const int4 d0 = cb_chain[2 * bi], d1 = cb_chain[2 * bi + 1];
-                c0 = d0.y; w = d0.z; nR = d0.w; rows_off = d1.x; h1 = d1.z;
-            } else {
-                c0 = P.sn_start[s]; w = P.sn_start[s + 1] - c0;
-                rows_off = P.rows_ptr[s]; nR = P.rows_ptr[s + 1] - rows_off;
-                if (bi >= 0) h1 = P.big[bi].h1;
+    Ctx wctx = ctx;
+    wctx.tid = tid & 31;
+    wctx.nthr = 32;
+    wctx.warp_scope = 1;
+    // generic forward step of a supernode that is not on the shared-memory path (scope: warp or CTA)
+    auto forward_generic = [&](const Ctx &c, int s) {
+        const Ctx &ctx = c;
+        const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+        const int nrow = w + (P.rows_ptr[s + 1] - P.rows_ptr[s]);
+        PAR_FOR(j, w) {   // pull from small (non-leaf, non-shared-memory) descendants
+            double acc = 0.0;
+            for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
+                const FwdEntry fe = P.fwd[q];
+                const double *Ld = pan + fe.off;
+                for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
             }
-            const int nrow = w + nR;
-            if (bi >= 0) {
-                const int *__restrict__ R = P.rows + rows_off;
-                // (contributions of the small descendants were pulled in bulk after their phases)
-                const int rI = (tid >> 2) < nR ? R[tid >> 2] : 0;      // row index of this thread's push row, in flight early
-                double y0 = 0.0, y1 = 0.0;      // warp 0: unknowns lane, lane + 32 (w <= 64)
-                if (wid == 0) { y0 = lane < w ? xs[c0 + lane] : 0.0; y1 = lane + 32 < w ? xs[c0 + lane + 32] : 0.0; }
-                for (int k0 = 0; k0 < w; k0 = (k0 == 0 ? h1 : w)) {
-                    const int k1 = k0 == 0 ? h1 : w;
-                    issue();                                  // the slot of the previous part is free (barrier above / below)
-                    const double *L = cb_dyn_smem + (buf_off + acquire() * buf_len - k0 * nrow);  // column k of the panel at L + k * nrow
-                        if (wid == 0) {      // L_tt y = v, unit lower triangular (zeros stored on and above the diagonal)
-                        const double *Lk0 = L + k0 * nrow + min(lane, nrow - 1), *Lk1 = L + k0 * nrow + min(lane + 32, nrow - 1);
-                        const int ka = min(k1, 32);
-                        int k = k0;
-#pragma unroll 4
-                        for (; k < ka; k++) {
-                            const double l0 = *Lk0, l1 = *Lk1;
-                            const double yk = __shfl_sync(0xffffffffu, y0, k);
-                            y0 -= l0 * yk;
-                            y1 -= l1 * yk;
-                            Lk0 += nrow; Lk1 += nrow;
-                        }
-#pragma unroll 4
-                        for (; k < k1; k++) {     // pivots 32 .. 63 live in y1 and only touch y1
-                            const double l1 = *Lk1;
-                            const double yk = __shfl_sync(0xffffffffu, y1, k - 32);
-                            y1 -= l1 * yk;
-                            Lk1 += nrow;
-                        }
-                        // y[k0 .. k1) are final
-                        if (lane >= k0 && lane < k1) { yv[lane] = y0; xs[c0 + lane] = y0; }
-                        if (lane + 32 >= k0 && lane + 32 < k1) { yv[lane + 32] = y1; xs[c0 + lane + 32] = y1; }
-                    }
-                        __syncthreads();
-                    {   // push x[R] -= L_R[:, k0:k1) y[k0:k1), four threads per row
-                        const int part = tid & 3;
-                        for (int base = 0; base < nR; base += nthr >> 2) {
-                            const int i = base + (tid >> 2);
-                            double a0 = 0.0, a1 = 0.0;      // two accumulators per thread
-                            if (i < nR) {
-                                const double *Lr = L + w + i + (k0 + part) * nrow;
-                                const double *yp = yv + k0 + part;
-                                const int cnt = (k1 - k0 - part + 3) >> 2;
-                                int j = 0;
-                                for (; j + 1 < cnt; j += 2) {
-                                    a0 += Lr[0] * yp[0];
-                                    a1 += Lr[4 * nrow] * yp[4];
-                                    Lr += 8 * nrow;
-                                    yp += 8;
-                                }
-                                if (j < cnt) a0 += Lr[0] * yp[0];
-                            }
-                            double acc = a0 + a1;
-                            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                            if (part == 0 && i < nR) xs[base == 0 ? rI : R[i]] -= acc;
-                        }
-                    }
-                    __syncthreads();
-                    }
-                return;
-            }
-            PAR_FOR(j, w) {   // pull from small (non-leaf, non-shared-memory) descendants
-                double acc = 0.0;
-                for (int q = P.fwd_ptr[c0 + j]; q < P.fwd_ptr[c0 + j + 1]; q++) {
-                    const FwdEntry fe = P.fwd[q];
-                    const double *Ld = pan + fe.off;
-                    for (int k = 0; k < fe.width; k++) acc += Ld[(long long)k * fe.stride] * xs[fe.col0 + k];
-                }
-                if (acc != 0.0) xs[c0 + j] -= acc;
-            }
-            const double *Ps = pan + P.panel_off[s];
-            for (int k = 0; k + 1 < w; k++) {
-                ctx.sync();
-                const double xk = xs[c0 + k];
-                PAR_FOR(i, w - 1 - k) xs[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
-            }
+            if (acc != 0.0) xs[c0 + j] -= acc;
+        }
+        const double *Ps = pan + P.panel_off[s];
+        for (int k = 0; k + 1 < w; k++) {
             ctx.sync();
-        },
-        [&](const Ctx &, int, int, int, int) {},
-        [&](int pi, int mode) {      // bulk pull: the finished phase's small supernodes -> pivot columns of chain supernodes
-            ps.stop(mode == 1 ? PROF_SF_SWEEP : PROF_SF_OTHER);      // (counters: chain supernodes / small supernodes)
-            const int r0 = cb_phase_n > 0 ? cb_pphase[pi] : P.pphase_ptr[pi], r1 = cb_phase_n > 0 ? cb_pphase[pi + 1] : P.pphase_ptr[pi + 1];
-            if (mode == 2 || r1 == r0) return;
+            const double xk = xs[c0 + k];
+            PAR_FOR(i, w - 1 - k) xs[c0 + k + 1 + i] -= Ps[(k + 1 + i) + (long long)k * nrow] * xk;
+        }
+        ctx.sync();
+    };
+    const int nph = P.nphases;
+    for (int pi = 0; pi < nph; pi++) {
+        const Phase ph = load_phase(P, pi);
+        int last = pi;
+        if (ph.mode == 1) {
+            if (ph.ebegin == pi + 1) {                            // a chain run starts here
+                last = ph.eend - 1;
+                const Phase pl = load_phase(P, last);
+                chain_run_forward(P, st, ph.first_big, pl.first_big + (pl.end - pl.begin) - ph.first_big, xs, yv, prof);
+            } else {
+                for (int q = ph.begin; q < ph.end; q++) {
+                    const int s = P.order[q], bi = P.big_index[s];
+                    if (bi >= 0) chain_run_forward(P, st, bi, 1, xs, yv, prof);
+                    else { forward_generic(ctx, s); __syncthreads(); }
+                }
+            }
+            ps.stop(PROF_SF_SWEEP);                               // (counter: chain supernodes)
+        } else if (ph.mode == 0) {
+            for (int q = ph.begin + wid; q < ph.end; q += nw) forward_generic(wctx, P.order[q]);
+            __syncthreads();
+            ps.stop(PROF_SF_OTHER);                               // (counter: small supernodes)
+        }
+        pi = last;
+        // bulk pull: the finished phase's small supernodes -> pivot columns of chain supernodes
+        const int r0 = cb_phase_n > 0 ? cb_pphase[pi] : P.pphase_ptr[pi], r1 = cb_phase_n > 0 ? cb_pphase[pi + 1] : P.pphase_ptr[pi + 1];
+        if (ph.mode != 2 && r1 > r0) {
             const int4 *__restrict__ rowi = reinterpret_cast<const int4 *>(P.prow);
             for (int r = r0 + tid; r < r1; r += nthr) {
                 const int4 ri = rowi[r];
@@ -1268,110 +1544,55 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                 xs[ri.x] -= acc;
             }
             __syncthreads();
-        });
+        }
+    }
     for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
     ps.stop(PROF_SF_PUSH);                                        // (counter: D^-1 scaling and bulk pulls after the last phase)
-    parts = P.parts_bwd;
-    nparts = P.nparts_bwd;
-    next_part = 0;
-    issue();
-    for_each_supernode(
-        ctx, P, false,
-        [&](const Ctx &c, int s, int hint) {
-            const Ctx &ctx = c;
-            const int bi = c.warp_scope ? -1 : (hint != -2 ? hint : P.big_index[s]);
-            int c0, w, nR, rows_off, h1 = 0;
-            if (bi >= 0 && bi < cb_chain_n) {
-                const int4 d0 = cb_chain[2 * bi], d1 = cb_chain[2 * bi + 1];
-                c0 = d0.y; w = d0.z; nR = d0.w; rows_off = d1.x; h1 = d1.z;
-            } else {
-                c0 = P.sn_start[s]; w = P.sn_start[s + 1] - c0;
-                rows_off = P.rows_ptr[s]; nR = P.rows_ptr[s + 1] - rows_off;
-                if (bi >= 0) h1 = P.big[bi].h1;
-            }
-            const int nrow = w + nR;
-            const int *__restrict__ R = P.rows + rows_off;
-            if (bi >= 0) {
-                double z0 = 0.0, z1 = 0.0;      // warp 0: unknowns lane, lane + 32
-                if (wid == 0) { z0 = lane < w ? xs[c0 + lane] : 0.0; z1 = lane + 32 < w ? xs[c0 + lane + 32] : 0.0; }
-                for (int i = tid; i < nR; i += nthr) xr[i] = xs[R[i]];      // x[R] (final), staged once for both parts
-                __syncthreads();
-                for (int k1 = w; k1 > 0; k1 = (k1 == w && h1 < w ? h1 : 0)) {     // column parts in reverse order
-                    const int k0 = (k1 == w && h1 < w) ? h1 : 0;
-                    issue();
-                    const double *L = cb_dyn_smem + (buf_off + acquire() * buf_len - k0 * nrow);
-                    {   // t_k = sum_{r >= k1} L[r, k] x_r for the columns k in [k0, k1) of this part: rows k1 .. w-1 are the
-                        // pivots of the part solved before (final in xs), rows w .. are R; four threads per column
-                        const int part = tid & 3;
-                        for (int base = k0; base < k1; base += nthr >> 2) {
-                            const int k = base + (tid >> 2);
-                            double a0 = 0.0, a1 = 0.0;
-                            if (k < k1) {
-                                const double *Lc = L + k * nrow;
-                                const double *xp = xs + c0;
-                                int r = k1 + part;
-                                for (; r + 4 < w; r += 8) { a0 += Lc[r] * xp[r]; a1 += Lc[r + 4] * xp[r + 4]; }   // pivots solved before
-                                if (r < w) { a0 += Lc[r] * xp[r]; r += 4; }
-                                const double *xq = xr - w;                                                     // rows R
-                                for (; r + 4 < nrow; r += 8) { a0 += Lc[r] * xq[r]; a1 += Lc[r + 4] * xq[r + 4]; }
-                                if (r < nrow) a0 += Lc[r] * xq[r];
-                            }
-                            double acc = a0 + a1;
-                            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                            if (part == 0 && k < k1) yv[k] = acc;
-                        }
-                    }
-                    __syncthreads();
-                        if (wid == 0) {      // L_tt' z = v restricted to the part: unit upper triangular, columns k1-1 .. k0
-                        if (lane >= k0 && lane < k1) z0 -= yv[lane];
-                        if (lane + 32 >= k0 && lane + 32 < k1) z1 -= yv[lane + 32];
-                        // row k of the block: column `lane` (zeros on and above the diagonal); lanes whose column is not
-                        // in this part read a zero cell with stride 0
-                        const bool in0 = lane >= k0 && lane < k1, in1 = lane + 32 >= k0 && lane + 32 < k1;
-                        const double *p0 = in0 ? L + lane * nrow + (k1 - 1) : zero_cell;
-                        const double *p1 = in1 ? L + (lane + 32) * nrow + (k1 - 1) : zero_cell;
-                        const int s0 = in0 ? 1 : 0, s1 = in1 ? 1 : 0;
-                        int k = k1 - 1;
-#pragma unroll 4
-                        for (; k > k0 && k >= 32; k--) {
-                            const double l0 = *p0, l1 = *p1;
-                            const double zk = __shfl_sync(0xffffffffu, z1, k - 32);
-                            z0 -= l0 * zk;
-                            z1 -= l1 * zk;
-                            p0 -= s0; p1 -= s1;
-                        }
-#pragma unroll 4
-                        for (; k > k0; k--) {     // pivots below 32 only touch z0
-                            const double l0 = *p0;
-                            const double zk = __shfl_sync(0xffffffffu, z0, k);
-                            z0 -= l0 * zk;
-                            p0 -= s0;
-                        }
-                        if (lane >= k0 && lane < k1) xs[c0 + lane] = z0;
-                        if (lane + 32 >= k0 && lane + 32 < k1) xs[c0 + lane + 32] = z1;
-                    }
-                        __syncthreads();
-                }
-                return;
-            }
-            const double *Ps = pan + P.panel_off[s];
-            PAR_FOR(k, w) {
-                double acc = 0.0;
-                const double *col = Ps + (long long)k * nrow + w;
-                for (int i = 0; i < nR; i++) acc += col[i] * xs[R[i]];
-                xs[c0 + k] -= acc;
-            }
-            for (int k = w - 1; k > 0; k--) {
-                ctx.sync();
-                const double xk = xs[c0 + k];
-                PAR_FOR(i, k) xs[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
-            }
+    st = PartStream{pan, P.parts_bwd, P.nparts_bwd, 0, 0, st.base + (unsigned)st.nparts, buf_off, buf_len};
+    part_prefetch(st, leader);
+    auto backward_generic = [&](const Ctx &c, int s) {
+        const Ctx &ctx = c;
+        const int c0 = P.sn_start[s], w = P.sn_start[s + 1] - c0;
+        const int rows_off = P.rows_ptr[s], nR = P.rows_ptr[s + 1] - rows_off, nrow = w + nR;
+        const int *__restrict__ R = P.rows + rows_off;
+        const double *Ps = pan + P.panel_off[s];
+        PAR_FOR(k, w) {
+            double acc = 0.0;
+            const double *col = Ps + (long long)k * nrow + w;
+            for (int i = 0; i < nR; i++) acc += col[i] * xs[R[i]];
+            xs[c0 + k] -= acc;
+        }
+        for (int k = w - 1; k > 0; k--) {
             ctx.sync();
-        },
-        [&](const Ctx &c, int begin, int end, int, int) {   // singleton leaves: four lanes per leaf
+            const double xk = xs[c0 + k];
+            PAR_FOR(i, k) xs[c0 + i] -= Ps[k + (long long)i * nrow] * xk;
+        }
+        ctx.sync();
+    };
+    for (int pi = nph - 1; pi >= 0; pi--) {
+        const Phase ph = load_phase(P, pi);
+        if (ph.mode == 1) {
+            if (ph.eend == pi + 1) {                              // the last phase of a chain run: the run is walked backwards
+                const int first = ph.ebegin - 1;
+                const Phase pf = load_phase(P, first);
+                chain_run_backward(P, st, pf.first_big, ph.first_big + (ph.end - ph.begin) - pf.first_big, xs, yv, xr, zero_cell, prof);
+                pi = first;
+            } else {
+                for (int q = ph.end - 1; q >= ph.begin; q--) {
+                    const int s = P.order[q], bi = P.big_index[s];
+                    if (bi >= 0) chain_run_backward(P, st, bi, 1, xs, yv, xr, zero_cell, prof);
+                    else { backward_generic(ctx, s); __syncthreads(); }
+                }
+            }
+            ps.stop(PROF_SB_SWEEP);                               // (counter: chain supernodes)
+        } else if (ph.mode == 0) {
+            for (int q = ph.begin + wid; q < ph.end; q += nw) backward_generic(wctx, P.order[q]);
+            __syncthreads();
+            ps.stop(PROF_SB_GATHER);                              // (counter: small supernodes)
+        } else {      // singleton leaves: four lanes per leaf
+            const int begin = ph.begin, end = ph.end;
             const int4 *__restrict__ info = reinterpret_cast<const int4 *>(P.leaf_info) + begin;
             const int *__restrict__ rows = P.rows;
             const int sub = tid & 3, grp = tid >> 2, ngrp = nthr >> 2, cnt = end - begin;
@@ -1402,15 +1623,14 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                 if (sub == 0 && q < cnt) xs[li.x] -= acc;
                 li = lin;
             }
-            (void)c;
             __syncthreads();
             ps.stop(PROF_SB_LEAVES);
-        },
-        [&](int, int mode) { if (mode != 2) ps.stop(mode == 1 ? PROF_SB_SWEEP : PROF_SB_GATHER); });   // (counters: chain / small)
+        }
+    }
     for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
     if (tid == 0 && istat) istat[I_SOLVES]++;
     __syncthreads();
-    if (tid == 0) cb_bar_uses = issued;
+    if (tid == 0) cb_bar_uses = st.base + (unsigned)st.nparts;
     __syncthreads();
     pt.stop(PROF_SOLVE_BWD);
     ps.stop(PROF_SB_OTHER);                                       // (counter: permutation scatter)
@@ -1944,11 +2164,19 @@ CB_DEVN int search_direction(const Ctx &ctx, const DevProblem &P, const Inst &I,
         if (ctx.tid == 0) I.istat[I_REFINE_OK] = ok ? 1 : 0;
         ctx.sync();
         if (!ok) {
-            if (I.krylov == nullptr) return ST_REFINEMENT_FAILURE;
+            if (I.krylov == nullptr) {
+                if (ctx.tid == 0) I.istat[I_UNREFINED_STEPS]++;
+                ctx.sync();
+                return ST_REFINEMENT_FAILURE;
+            }
             bool gok = gmres_fallback(ctx, P, I, o);
             if (ctx.tid == 0) { I.istat[I_USED_FALLBACK] = 1; I.istat[I_FALLBACKS]++; }
             ctx.sync();
-            if (!gok) return ST_REFINEMENT_FAILURE;
+            if (!gok) {      // neither refinement nor the fallback reached the tolerance: counted, reported as status 2
+                if (ctx.tid == 0) I.istat[I_UNREFINED_STEPS]++;
+                ctx.sync();
+                return ST_REFINEMENT_FAILURE;
+            }
         }
     }
     return ST_OK;

@@ -225,6 +225,9 @@ CB_DEVN int newton_iteration_lq(const Ctx &ctx, const DevProblem &P, const Inst 
     // (second derivatives and Jacobians are constant for the LQ family: nothing to re-evaluate, solve.jl:175-185)
     int st = search_direction(ctx, P, I, o);
     if (st == ST_INERTIA_FAILURE) return -ST_INERTIA_FAILURE;
+    // ST_REFINEMENT_FAILURE is not an error of solve!: the reference takes whatever `J \ R` returns after a failed
+    // refinement (search_direction.jl:22) and carries on; here the step of the fallback is taken likewise and the event is
+    // counted in I_UNREFINED_STEPS (cb200_get_stats) so that callers can see it.
     pt.start();
     st = cone_search(ctx, P, I, o);
     if (st != ST_OK) return -ST_CONE_SEARCH_FAILURE;

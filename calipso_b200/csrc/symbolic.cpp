@@ -505,11 +505,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
                                   (int)panel_off[t], big[bi].h1, 0});
     }
     for (Phase &ph : phases) ph.first_big = ph.mode == 1 ? big_index[order[ph.begin]] : -1;
-    big_seq_bwd.clear();
-    for (int pi = (int)phases.size() - 1; pi >= 0; pi--)
-        if (phases[pi].mode == 1)
-            for (int q = phases[pi].begin; q < phases[pi].end; q++)
-                if (big_index[order[q]] >= 0) big_seq_bwd.push_back(order[q]);
+    big_seq_bwd.assign(big_seq.rbegin(), big_seq.rend());     // the backward solve visits them in exactly the reverse order
     {   // shared-memory solve: the permuted vector, two part buffers (TMA double buffering), one pivot window
         max_sb_doubles = (max_sb_doubles + 1) & ~1;
         int max_nR_big = 0;
@@ -597,6 +593,26 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         max_big_nR = 0;
         for (int t = 0; t < ns; t++)
             if (big_index[t] >= 0) max_big_nR = std::max(max_big_nR, rows_ptr[t + 1] - rows_ptr[t]);
+    }
+    // chain runs: maximal sequences of consecutive CTA-scope phases whose tasks are all on the shared-memory path and
+    // between which no bulk pull is scheduled.  The solves process a run without CTA-wide barriers (one warp runs the
+    // triangular sweeps, the others the rectangular parts, device_core.h).  Stored in the otherwise unused fields of the
+    // mode-1 phase records: ebegin = first phase of the run + 1, eend = last phase of the run + 1 (0: not in a run).
+    {
+        const int np = (int)phases.size();
+        auto all_big = [&](int pi) {
+            if (phases[pi].mode != 1) return false;
+            for (int q = phases[pi].begin; q < phases[pi].end; q++)
+                if (big_index[order[q]] < 0) return false;
+            return true;
+        };
+        for (int pi = 0; pi < np;) {
+            if (!all_big(pi)) { if (phases[pi].mode == 1) phases[pi].ebegin = phases[pi].eend = 0; pi++; continue; }
+            int pj = pi;
+            while (pj + 1 < np && all_big(pj + 1) && pphase_ptr[pj + 1] == pphase_ptr[pj]) pj++;
+            for (int k = pi; k <= pj; k++) { phases[k].ebegin = pi + 1; phases[k].eend = pj + 1; }
+            pi = pj + 1;
+        }
     }
     lcsr_cols.clear();
     lcsr_rowinfo.clear();

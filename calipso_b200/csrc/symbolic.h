@@ -22,7 +22,8 @@ struct Phase {
     int mode;        // 0: one warp per supernode (tasks run concurrently); 1: whole CTA per supernode (sequential);
                      // 2: singleton leaves (width 1, no incoming update), one thread per supernode
     int begin, end;  // range in Symbolic::order
-    int ebegin, eend; // mode 2: range in the flat leaf-entry lists (leaf_e_off / leaf_e_col / leaf_e_pos)
+    int ebegin, eend; // mode 2: range in the flat leaf-entry lists (leaf_e_off / leaf_e_col / leaf_e_pos);
+                      // mode 1: chain run this phase belongs to (first phase + 1, last phase + 1; 0 = none), see analyze()
     int first_big;   // mode 1: index in big[] of the phase's first task (-1: not on the shared-memory path)
 };
 
@@ -134,7 +135,7 @@ struct Symbolic {
     std::vector<int> dg_dst, dg_ptr;          // per group: offset in the work area S; [groups + 1] range in dg_src / dg_piv
     std::vector<int> dg_src, dg_piv;          // per entry: panel offset of l, pivot column of d
     std::vector<int> big_seq;     // shared-memory supernodes in forward schedule order (TMA prefetch chain)
-    std::vector<int> big_seq_bwd; // ... and in backward schedule order (phases reversed, tasks of a phase ascending)
+    std::vector<int> big_seq_bwd; // ... and in backward order (the exact reverse)
     std::vector<int> parts_fwd, parts_bwd;   // TMA copies of the solves in issue order: (panel offset, doubles) pairs
     int max_sb_doubles = 0;       // largest part (see BigTarget::h1) of a shared-memory supernode's panel
     int solve_smem = 0;           // 1: x and two solve-block buffers fit in the CTA work area (ldl_solve fast path)

@@ -367,6 +367,7 @@ class Solver:
         o.W_val, o.G_val, o.C_val = np.zeros(nW), np.zeros(nG), np.zeros(nC)
         self.cone_product = np.zeros(k.p)
         self.iterations = 0
+        self.unrefined_steps = 0
         self.log = []
 
     # evaluate!(problem, methods, idx, point, parameters; flags...)
@@ -471,6 +472,12 @@ def solve(solver: Solver) -> bool:
                 raise RuntimeError("inertia correction failure")          # inertia.jl:72
             if st["status"] == 3:
                 raise RuntimeError("cone search failure")                 # solve.jl:210,220
+            if st["status"] == 2:
+                # refinement and the fallback both missed the tolerance: the reference takes the `J \ R` step as it
+                # comes (search_direction.jl:22); the step is taken here too, and the event is made visible
+                import warnings
+                warnings.warn("iterative refinement failure: search direction not refined to tolerance")
+                s_.unrefined_steps += 1
             sc = {kk: v[0] for kk, v in k.scalars().items()}
             step_size = sc["step_size"]
             step = k.get("STEP")[0]
@@ -589,8 +596,9 @@ class LDLSolver:
         import scipy.sparse as sp
         if Amat is None:
             return self._values
-        if isinstance(Amat, np.ndarray) and Amat.ndim <= 2 and Amat.shape[-1] == self.nnz:
-            return f64(Amat).reshape(self.batch, self.nnz)
+        if isinstance(Amat, np.ndarray) and (Amat.shape == (self.nnz,) or Amat.shape == (self.batch, self.nnz)) \
+                and Amat.shape != (self.N, self.N):
+            return np.ascontiguousarray(np.broadcast_to(f64(Amat).reshape(-1, self.nnz), (self.batch, self.nnz)))   # packed values
         U = sp.triu(sp.csc_matrix(Amat)).tocsc()
         U.sort_indices()
         if not (np.array_equal(U.indptr, self.colptr) and np.array_equal(U.indices, self.rowval)):

@@ -102,7 +102,7 @@ enum {
     CB200_I_INERTIA_POS = 0, CB200_I_INERTIA_NEG, CB200_I_INERTIA_ZERO, CB200_I_TRIALS, CB200_I_REFINE,
     CB200_I_REFINE_OK, CB200_I_KS, CB200_I_KT, CB200_I_STATUS, CB200_I_USED_FALLBACK, CB200_I_FALLBACKS,
     CB200_I_TOTAL_ITERATIONS, CB200_I_OUTER, CB200_I_LINE_SEARCH, CB200_I_CONVERGED, CB200_I_GMRES_ITERS,
-    CB200_I_FILTER_INDEX, CB200_I_INNER, CB200_I_FACTORIZATIONS, CB200_I_SOLVES, CB200_I_COUNT = 24
+    CB200_I_FILTER_INDEX, CB200_I_INNER, CB200_I_FACTORIZATIONS, CB200_I_SOLVES, CB200_I_UNREFINED_STEPS, CB200_I_COUNT = 24
 };
 
 /* evaluate! flags (src/solver/evaluate.jl keyword arguments) for cb200_lq_evaluate */

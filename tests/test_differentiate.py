@@ -170,7 +170,7 @@ def double_integrator(seed=0, T=5):
     return P, Gm, wd, ix, iu
 
 
-@pytest.mark.parametrize("backend", ["emul"])     # (device code compiled for the host; the CUDA run of this case is still to do)
+@pytest.mark.parametrize("backend", backends.BACKENDS)
 def test_double_integrator_sensitivities(backend):
     """test/examples/double_integrator.jl:64-165: solve with the example's tight tolerances, then the sensitivities of the
     primal variables agree with -L_zz^-1 L_z,theta (z = [x; y]) to 1e-3 (:164)."""

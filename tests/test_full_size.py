@@ -1,8 +1,12 @@
-"""BASELINE.json's full sizes (cfg3: LQC(40,36,12,100), N = 4584, total = 8496) on the GPU, checked through
-size-independent properties instead of the (slow) oracle -- the same properties the reference's own unit test pins
-(test/solver/problem.jl:100-211): expected inertia (n, m+p, 0) (inertia.jl:7-11), refinement drives the FULL Newton
-system to ||R - J step||_inf <= 1e-10 (:207-211), the reduced LDL' solve reproduces K x = b, and a complete solve!
-meets the four stopping criteria (e.g. test/solver/wachter.jl:36-45)."""
+"""BASELINE.json's full sizes (cfg3: LQC(40,36,12,100), N = 4584, total = 8496; cfg4: a batch of 64 cfg3 instances) on the GPU:
+
+* against the ORACLE on the same seeded inputs -- complete solve! of cfg3 seeds and of a cfg4 batch (per-instance iteration,
+  outer-iteration and fallback counts exact, solution to 1e-8; the per-step comparison of the pieces is
+  tests/test_parity_kkt.py::test_newton_step_pieces_cfg3);
+* through the size-independent properties the reference's own unit test pins (test/solver/problem.jl:100-211): expected
+  inertia (n, m+p, 0) (inertia.jl:7-11), refinement drives the FULL Newton system to ||R - J step||_inf <= 1e-10 (:207-211),
+  the reduced LDL' solve reproduces K x = b, and a complete solve! meets the four stopping criteria (e.g.
+  test/solver/wachter.jl:36-45)."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -10,8 +14,60 @@ import scipy.sparse as sp
 import backends
 from calipso_b200 import lqc
 from calipso_b200.solver import BatchKKT, LDLSolver
+from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+
+
+def _oracle_solve(P, perm):
+    o = orc.from_problem(P, perm=perm)
+    o.use_superlu_fallback()
+    o.initialize(P.x0)
+    assert o.solve() == 1
+    return o
+
+
+def _compare_batch_with_oracle(k, Ps):
+    """Every instance of a solved batch against its own oracle solve!: integer outcomes exact, floating point 1e-8."""
+    perm, _, _ = k.symbolic()
+    W, lam, st, sc = k.get("POINT"), k.get("DUAL"), k.stats(), k.scalars()
+    for i, P in enumerate(Ps):
+        o = _oracle_solve(P, perm)
+        assert st["total_iterations"][i] == o.stats["total_iterations"], i
+        assert st["outer"][i] == o.stats["outer"], i
+        assert st["fallbacks"][i] == o.stats["lu_fallbacks"], i
+        assert np.abs(W[i] - o.solution).max() <= RTOL * np.abs(o.solution).max(), i
+        assert np.abs(lam[i] - o.dual).max() <= RTOL * max(np.abs(o.dual).max(), 1.0), i
+        osc = o.scalars()
+        assert sc["kappa"][i] == pytest.approx(osc["kappa"], rel=1e-13) and sc["rho"][i] == pytest.approx(osc["rho"], rel=1e-13)
+
+
+@pytest.mark.parametrize("first_seed", [0, 8])
+def test_cfg3_solve_matches_oracle(first_seed):
+    """Complete solve! of eight cfg3 seeds per case (one instance per CTA) against the oracle."""
+    Ps = [lqc.cfg3(first_seed + i) for i in range(8)]
+    k = BatchKKT(Ps[0], batch=8, binding=backends.binding("cuda"))
+    k.load_lq(Ps)
+    k.initialize(np.stack([P.x0 for P in Ps]))
+    k.lq_begin()
+    r = k.lq_solve(max_steps=400, check_every=400)
+    assert r["converged"] == 8 and r["running"] == 0 and r["error"] == 0
+    _compare_batch_with_oracle(k, Ps)
+
+
+def test_cfg4_batch_matches_oracle():
+    """BASELINE.json configs[4]: the batch of 64 independent cfg3 instances (seeds 0 .. 63, the blocks of 8 a rank owns at 8
+    GPUs) solved in one handle (one instance per SM: the 512-thread kernels), every instance against its oracle solve!."""
+    B = 64
+    Ps = [lqc.cfg3(i) for i in range(B)]
+    k = BatchKKT(Ps[0], batch=B, binding=backends.binding("cuda"))
+    k.load_lq(Ps)
+    k.initialize(np.stack([P.x0 for P in Ps]))
+    k.lq_begin()
+    r = k.lq_solve(max_steps=400, check_every=400)
+    assert r["converged"] == B and r["running"] == 0 and r["error"] == 0
+    _compare_batch_with_oracle(k, Ps)
 
 
 def test_cfg3_search_direction_properties():

@@ -3,6 +3,8 @@
 Tolerances: integer outcomes (inertia, regularisation trials, refinement passes, halving counts, iteration counts)
 exact; floating point 1e-8 relative (BASELINE.json north_star) -- measured differences are ~1e-12.
 """
+import itertools
+
 import numpy as np
 import pytest
 
@@ -54,7 +56,19 @@ def push_state(k, o, b=0):
 @pytest.mark.parametrize("backend", backends.BACKENDS)
 @pytest.mark.parametrize("make,iters", [(lqc.tiny, 0), (lqc.tiny, 3), (lqc.tiny, 6), (lqc.cfg2, 2), (lqc.cfg2, 5)])
 def test_newton_step_pieces(backend, make, iters):
-    P = make()
+    check_newton_step_pieces(backend, make(), iters)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,iters", [(s, it) for s in range(8) for it in ((2, 6) if s % 2 == 0 else (4,))])
+def test_newton_step_pieces_cfg3(seed, iters):
+    """BASELINE.json's headline configuration (cfg3: LQC(40,36,12,100), N = 4584) against the oracle, eight seeds: residual,
+    reductions, inertia / trial / refinement / halving counts (exact), search direction and candidate (1e-8), L and D against
+    QDLDL with the same ordering."""
+    check_newton_step_pieces("cuda", lqc.cfg3(seed), iters)
+
+
+def check_newton_step_pieces(backend, P, iters):
     k = BatchKKT(P, binding=backends.binding(backend))
     perm, _, _ = k.symbolic()
     o = oracle_at_iteration(P, iters, perm=perm)
@@ -69,7 +83,8 @@ def test_newton_step_pieces(backend, make, iters):
     # cone! + residual!
     k.cone(barrier=True, barrier_gradient=True, product=True)
     k.residual()
-    assert rel(k.get("RESIDUAL")[0], o.residual) < 1e-11
+    # (near convergence the residual is a difference of O(1) terms: its error relative to its own magnitude reaches ~1e-11)
+    assert rel(k.get("RESIDUAL")[0], o.residual) < 1e-10
     assert rel(k.get("BARRIER_GRADIENT")[0], o.barrier_gradient) < 1e-11
     assert rel(k.get("CONE_PRODUCT")[0], o.cone_product) < 1e-11
     sc = k.scalars()
@@ -165,7 +180,7 @@ def test_lq_solve_on_device_matches_oracle(backend, make):
     if make is lqc.cfg2_hard:
         assert st["fallbacks"] > 0          # the GMRES stand-in for `J \\ R` (search_direction.jl:22) was exercised
     w = k.get("POINT")[0]
-    assert rel(w, o.solution) < 1e-6
+    assert rel(w, o.solution) < RTOL          # whole solve!: measured 1e-15 .. 1e-13 (the refined steps agree to ~1e-12)
     sc = k.scalars()
     # kappa goes through pow(kappa, 1.5): device libm vs host libm may differ in the last ulp
     assert sc["kappa"][0] == pytest.approx(o.scalars()["kappa"], rel=1e-13)
@@ -190,7 +205,7 @@ def test_batch_of_instances_is_independent(backend):
         o.use_superlu_fallback()
         o.initialize(P.x0)
         assert o.solve() == 1
-        assert rel(W[i], o.solution) < 1e-6
+        assert rel(W[i], o.solution) < RTOL
         assert st["total_iterations"][i] == o.stats["total_iterations"]
 
 
@@ -219,14 +234,19 @@ def test_reference_solver_cases_through_host_callbacks(backend, name):
     o.initialize(P.x0)
     assert o.solve() == 1
     assert s.iterations == o.stats["total_iterations"]
-    assert rel(s.solution, o.solution) < 1e-6
+    assert rel(s.solution, o.solution) < RTOL
 
 
-@pytest.mark.parametrize("backend", backends.BACKENDS)
-def test_friction_cone_table(backend):
-    """test/solver/friction_cone.jl:19-63 (a subset of the 30 combinations; the oracle test runs all of them)."""
-    for v, mu, gamma in [([0.0, 1.0, 0.0], 0.5, 1.0), ([0.0, 1.0, 1.0], 1.0, 1.0), ([0.0, 10.0, 1.0], 0.5, 1.0),
-                         ([0.0, 0.0, 0.0], 0.0, 0.0)]:
+FRICTION_TABLE = list(itertools.product([[0.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 1.0, 1.0], [0.0, 10.0, 1.0]],
+                                        [0.0, 0.5, 1.0], [0.0, 1.0]))
+FRICTION_SUBSET = [([0.0, 1.0, 0.0], 0.5, 1.0), ([0.0, 1.0, 1.0], 1.0, 1.0), ([0.0, 10.0, 1.0], 0.5, 1.0), ([0.0, 0.0, 0.0], 0.0, 0.0)]
+
+
+@pytest.mark.parametrize("backend,table", [("emul", FRICTION_SUBSET), pytest.param("cuda", FRICTION_TABLE, marks=pytest.mark.gpu)])
+def test_friction_cone_table(backend, table):
+    """test/solver/friction_cone.jl:19-63: all 30 (v, mu, gamma) combinations on the GPU (a subset through the host
+    emulation, to keep the CPU suite short; the oracle test runs all of them too)."""
+    for v, mu, gamma in table:
         P = problems.friction(v, mu, gamma, np.random.default_rng(3).standard_normal(3))
         s = Solver(P, P.callback, binding=backends.binding(backend))
         initialize(s, P.x0)

@@ -519,6 +519,18 @@ extern "C" int cb200_info(const cb200_handle *h, long long *out)
     return 0;
 }
 
+extern "C" int cb200_amd_order(int N, const int *Ap, const int *Ai, int *perm)
+{
+    if (N < 0 || !Ap || !Ai || !perm) return fail("cb200_amd_order: invalid arguments");
+    for (int j = 0; j < N; j++)
+        for (int q = Ap[j]; q < Ap[j + 1]; q++)
+            if (Ai[q] < 0 || Ai[q] >= N || (q > Ap[j] && Ai[q] <= Ai[q - 1])) return fail("cb200_amd_order: rows must be sorted, unique and in range");
+    std::vector<int> p;
+    amd_order(N, Ap, Ai, p);
+    std::copy(p.begin(), p.end(), perm);
+    return 0;
+}
+
 extern "C" int cb200_get_symbolic(const cb200_handle *h, int *perm, int *etree, int *Lnz)
 {
     const Symbolic &S = h->sym();

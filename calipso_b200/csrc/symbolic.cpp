@@ -2,7 +2,9 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
+#include <string>
 
 namespace cb200 {
 
@@ -150,7 +152,14 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             seen[v] = 1;
         }
     } else {
-        minimum_degree(n, Ap, Ai, perm0);
+        // Two built-in orderings.  "amd" is the reference's own (amd(A), qdldl.jl:135; also available to callers through
+        // cb200_amd_order + the perm argument); "mindeg" (exact external degrees) keeps the constraint multipliers of a
+        // trajectory-optimisation KKT matrix as singleton leaves and gives one wide supernode per stage -- 42 levels instead
+        // of 196 on BASELINE's cfg3 at 11% more fill -- which is the better shape for one-CTA-per-instance numerics and
+        // therefore the default.  Results agree to rounding either way (any permutation gives the same solution).
+        const char *ord = getenv("CB200_ORDERING");
+        if (ord && std::string(ord) == "amd") amd_order(n, Ap, Ai, perm0);
+        else minimum_degree(n, Ap, Ai, perm0);
     }
     std::vector<int> iperm0(n);
     for (int k = 0; k < n; k++) iperm0[perm0[k]] = k;

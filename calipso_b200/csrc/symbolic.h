@@ -166,9 +166,12 @@ struct Symbolic {
                         int smem_budget_doubles = 9250);   // 74 KB + 2.6 KB static + 1 KB reserved, three CTAs per SM
 };
 
-// Approximate-minimum-degree stand-in: quotient-graph minimum degree with element absorption and exact external
-// degrees (ties -> lowest index).  Not SuiteSparse AMD (absent here; any fill-reducing order gives the same solution
-// to rounding).
+// Default ordering: approximate minimum degree (amd.cpp) -- the published AMD algorithm with SuiteSparse's conventions and
+// default controls, i.e. what the reference's `perm = amd(A)` (src/solver/qdldl.jl:135) computes.  Any triangle content;
+// perm[k] = index eliminated k-th.
+void amd_order(int n, const int *Ap, const int *Ai, std::vector<int> &perm, double dense_factor = 10.0, bool aggressive = true);
+// Alternative (CB200_ORDERING=mindeg): quotient-graph minimum degree with element absorption and exact external degrees
+// (ties -> lowest index); upper-triangular pattern.
 void minimum_degree(int n, const int *Ap, const int *Ai, std::vector<int> &perm);
 
 }  // namespace cb200

@@ -131,6 +131,11 @@ void cb200_destroy(cb200_handle *h); /* Julia finalizer */
 /* out[16]: N, total, nnz(K upper), nnz(L) (true fill), supernodes, levels, phases, max supernode width,
  * max panel rows, panel_total (doubles), sum Lnz^2, batch, n, m, p, nnz(W)+nnz(G)+nnz(C) */
 int cb200_info(const cb200_handle *h, long long *out);
+/* amd(A) of src/solver/qdldl.jl:135 (AMD.jl / SuiteSparse AMD, default controls) for an N x N CSC pattern with sorted rows
+ * (any triangle content; the ordering is that of A + A'): perm[k] = 0-based index eliminated k-th.  Host-only, no handle,
+ * no GPU.  Pass the result as `perm` to cb200_create / cb200_ldl_create to factor in the reference's own elimination
+ * order (the library's default ordering is a minimum-degree variant better suited to the device). */
+int cb200_amd_order(int N, const int *Ap, const int *Ai, int *perm);
 /* Appendix-B integer contract for parity tests: perm, etree, Lnz (each [N], 0-based, elimination order) */
 int cb200_get_symbolic(const cb200_handle *h, int *perm, int *etree, int *Lnz);
 /* L in QDLDL's CSC form (strictly lower, unit diagonal implied) and D of instance b, extracted from the supernodal

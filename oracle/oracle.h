@@ -60,6 +60,9 @@ long long orc_qdldl_factor_count(const orc_qdldl *F); /* numeric factorisations 
 
 /* stand-in ordering: exact minimum degree on the pattern of A+A' (ties -> lowest index) */
 void orc_min_degree(int n, const int *Ap, const int *Ai, int *perm);
+/* amd(A) of src/solver/qdldl.jl:135 (AMD.jl -> SuiteSparse amd_l_order, defaults dense = 10, aggressive = 1): restated in
+ * amd.c from the published algorithm.  Any triangle content; P[k] = index eliminated k-th.  Returns 0 on success. */
+int orc_amd_order(int n, const int *Ap, const int *Ai, int *P, double dense, int aggressive);
 
 /* ---------------------------------------------------------------- solver (src/solver/ *.jl) */
 

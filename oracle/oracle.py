@@ -51,7 +51,7 @@ EV_EQUALITY_DUAL_GRAD, EV_CONE_DUAL_GRAD, EV_HESSIAN, EV_EQUALITY_JAC, EV_CONE_J
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("qdldl.c", "solver.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("qdldl.c", "solver.c", "amd.c", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
     return so
@@ -79,6 +79,7 @@ def lib():
             getattr(L, "orc_qdldl_" + name).argtypes = [vp]
             getattr(L, "orc_qdldl_" + name).restype = c_dp
         L.orc_min_degree.argtypes = [C.c_int, c_ip, c_ip, c_ip]
+        L.orc_amd_order.argtypes = [C.c_int, c_ip, c_ip, c_ip, C.c_double, C.c_int]
         L.orc_options_default.argtypes = [C.POINTER(Options)]
         L.orc_solver_new.restype = vp
         L.orc_solver_new.argtypes = [C.c_int] * 5 + [c_ip] * 8 + [C.POINTER(Options)]
@@ -194,6 +195,15 @@ def min_degree(n, Ap, Ai):
     Ap, Ai = _i32(Ap), _i32(Ai)
     perm = np.zeros(n, dtype=np.int32)
     lib().orc_min_degree(n, _ip(Ap), _ip(Ai), _ip(perm))
+    return perm
+
+
+def amd(n, Ap, Ai, dense=10.0, aggressive=True):
+    """amd(A), src/solver/qdldl.jl:135: the restated SuiteSparse AMD ordering (oracle/amd.c) of a CSC pattern."""
+    Ap, Ai = _i32(Ap), _i32(Ai)
+    perm = np.zeros(n, dtype=np.int32)
+    if lib().orc_amd_order(n, _ip(Ap), _ip(Ai), _ip(perm), float(dense), int(aggressive)) != 0:
+        raise MemoryError("orc_amd_order failed")
     return perm
 
 

@@ -243,7 +243,7 @@ orc_qdldl *orc_qdldl_new(int n, const int *Ap, const int *Ai, const double *Ax, 
     if (perm)
         memcpy(F->perm, perm, sizeof(int) * (size_t)n);
     else
-        orc_min_degree(n, Ap, Ai, F->perm); /* stand-in for amd(A), qdldl.jl:135 */
+        if (orc_amd_order(n, Ap, Ai, F->perm, 10.0, 1) != 0) orc_min_degree(n, Ap, Ai, F->perm); /* amd(A), qdldl.jl:135 */
     for (int i = 0; i < n; i++) F->iperm[F->perm[i]] = i; /* invperm, qdldl.jl:143 */
     F->Ap = (int *)malloc(sizeof(int) * (size_t)(n + 1));
     F->Ai = (int *)malloc(sizeof(int) * (size_t)nnz);

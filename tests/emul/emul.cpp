@@ -162,6 +162,14 @@ extern "C" int cb200_info(const cb200_handle *h, long long *out)
     return 0;
 }
 
+extern "C" int cb200_amd_order(int N, const int *Ap, const int *Ai, int *perm)
+{
+    std::vector<int> p;
+    amd_order(N, Ap, Ai, p);
+    std::copy(p.begin(), p.end(), perm);
+    return 0;
+}
+
 extern "C" int cb200_get_symbolic(const cb200_handle *h, int *perm, int *etree, int *Lnz)
 {
     const Symbolic &S = h->sym();

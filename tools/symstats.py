@@ -11,7 +11,7 @@ from calipso_b200 import lqc
 
 so = "/tmp/ss/libsymstats.so"
 subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tools", "symstats.cpp"),
-                       os.path.join(ROOT, "calipso_b200", "csrc", "symbolic.cpp")])
+                       os.path.join(ROOT, "calipso_b200", "csrc", "symbolic.cpp"), os.path.join(ROOT, "calipso_b200", "csrc", "amd.cpp")])
 lib = C.CDLL(so)
 P = getattr(lqc, sys.argv[1] if len(sys.argv) > 1 else "cfg3")()
 ip = lambda a: np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int))

@@ -2,15 +2,17 @@
 """bench.py -- Newton iterations/s of CALIPSO's Newton/KKT hot path on B200 (BASELINE.json metric).
 
 One "step" = one complete solve! (src/solver/solve.jl:8-377) of a batch of independent cfg3-shaped instances
-(LQC(40,36,12,100), N = 4584, synthetic, seeded) resident on the GPU: every Newton iteration runs residual assembly,
-KKT assembly, supernodal LDL^T with inertia correction, refinement, cone search and the filter line search on the
-device.  value = Newton iterations completed by all instances of all ranks / device time (max over ranks).
+(LQC(40,36,12,100), N = 4584, synthetic, seeded; BASELINE.json configs[3]/[4]) resident on the GPU: every Newton iteration
+runs residual assembly, KKT assembly, supernodal LDL^T with inertia correction, refinement, cone search and the filter
+line search on the device.  value = Newton iterations completed by all instances of all ranks / device time (max over
+ranks).  e2e = the same complete solves through the C ABI from pinned HOST buffers: problem data and guesses are uploaded
+and solutions read back inside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
 
-Under torchrun (N > 1) every rank owns `--batch` instances (weak scaling, no data-path collective; one NCCL
-all-reduce of convergence counts per check).  `--impl reference` times the CPU oracle (the restated reference
-algorithm, reference schedule) on the host cores instead.
+Under torchrun (N > 1) every rank owns `--batch` instances (weak scaling, no data-path collective; one NCCL all-reduce of
+convergence counts per check).  `--impl reference` times the CPU oracle (the restated reference algorithm, reference
+schedule) on all host cores on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -31,56 +33,109 @@ from calipso_b200 import lqc  # noqa: E402
 
 LOCKSTEP = os.environ.get("CB200_LQ_LOCKSTEP", "0") not in ("", "0")   # one k_lq_step launch per Newton iteration (A/B)
 
-CFG = dict(T=40, n_x=36, n_u=12, n_soc=100)       # BASELINE.json configs[3] (cfg3)
 METRIC = "newton_iterations_per_second"
 UNIT = "Newton it/s"
+SHAPE = dict(T=40, n_x=36, n_u=12, n_soc=100, n=1908, m=1440, p=1236, N=4584, total=8496)     # cfg3
 
 
-def make_instances(count, first_seed):
-    return [lqc.cfg3(first_seed + i) for i in range(count)]
+def workload_config(batch, distinct, check_every):
+    """The `config` object of both arms (the reference arm runs a bounded sample of exactly this workload)."""
+    return dict(workload=f"cfg4-style batch of cfg3 LQC(T=40,n_x=36,n_u=12,n_soc=100) instances (BASELINE.json configs[3]/[4] "
+                         f"shape), {batch} per GPU, one complete solve! of every instance per step",
+                N=SHAPE["N"], total=SHAPE["total"], n=SHAPE["n"], m=SHAPE["m"], p=SHAPE["p"], batch_per_gpu=batch,
+                distinct_seeds_per_gpu=distinct, seeds="1000*3 + rank*distinct + i (calipso_b200/lqc.py)",
+                newton_iterations_per_launch_max=check_every,
+                schedule="lock-step (one launch per Newton iteration)" if LOCKSTEP else
+                         "independent (a launch carries up to check_every iterations of an instance)",
+                l2_policy="inputs larger than L2: per-GPU working set = batch x ~4.5 MB",
+                parallelism=f"instances sharded {batch}/GPU, NCCL all-reduce of convergence counts only")
 
 
 # ------------------------------------------------------------------------------------------------- CPU oracle legs
-def _oracle_worker(args):
-    seeds, reference_schedule, budget_s = args
+_W = {}      # per-process state of the oracle workers
+_NEXT = None  # shared ticket counter (created before the workers fork)
+
+
+def _oracle_prepare(args):
+    """(untimed) build the step's instances and their oracle solvers in this worker: generation, ordering, symbolic analysis"""
+    seeds, reference_schedule = args
     from oracle import oracle as orc
-    iters = 0
-    t0 = time.perf_counter()
-    solves = 0
-    kkt_ms = []
+    objs = []
     for s in seeds:
         P = lqc.cfg3(s)
         o = orc.from_problem(P, options=dict(reference_schedule=reference_schedule))
         o.use_superlu_fallback()
-        o.initialize(P.x0)
-        rc = o.solve()
-        iters += o.stats["total_iterations"] - 1
-        solves += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    return iters, time.perf_counter() - t0, solves
+        objs.append((o, P.x0.copy()))
+    _W[reference_schedule] = objs
+    return len(objs)
 
 
-def oracle_throughput(cores, seeds, reference_schedule, budget_s):
-    """Newton it/s of the oracle on `cores` host processes (one instance at a time per process)."""
-    import multiprocessing as mp
-    chunks = [seeds[i::cores] for i in range(cores)]
+def _oracle_solve_tickets(reference_schedule):
+    """(timed) this worker pulls instance tickets from the shared counter until the step's instances are used up:
+    initialize! + solve! of each; returns (Newton iterations, instances solved, busy seconds)"""
+    objs = _W[reference_schedule]
+    iters = solved = 0
     t0 = time.perf_counter()
-    if cores == 1:
-        res = [_oracle_worker((chunks[0], reference_schedule, budget_s))]
-    else:
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_oracle_worker, [(c, reference_schedule, budget_s) for c in chunks])
-    wall = time.perf_counter() - t0
-    iters = sum(r[0] for r in res)
-    solves = sum(r[2] for r in res)
-    return iters / wall, iters, solves, wall
+    while True:
+        with _NEXT.get_lock():
+            i = _NEXT.value
+            _NEXT.value = i + 1
+        if i >= len(objs):
+            break
+        o, x0 = objs[i]
+        o.initialize(x0)
+        o.solve()
+        iters += o.stats["total_iterations"] - 1
+        solved += 1
+    return iters, solved, time.perf_counter() - t0
 
 
-def oracle_kkt_solve_ms(seed=3000):
+class OraclePool:
+    """`cores` persistent worker processes sharing a step of `instances` prepared cfg3 instances (every worker holds all of
+    them; the instances of a step are handed out one at a time, so no worker idles while another still has several to do)."""
+
+    def __init__(self, cores, instances, first_seed=0):
+        import multiprocessing as mp
+        global _NEXT
+        self.cores, self.instances = cores, instances
+        self.seeds = [first_seed + i for i in range(instances)]
+        _NEXT = mp.get_context("fork").Value("i", 0)
+        self.pools = [mp.get_context("fork").Pool(1) for _ in range(cores)] if cores > 1 else None
+        self.ready = set()
+
+    def prepare(self, reference_schedule):
+        if reference_schedule in self.ready:
+            return
+        if self.pools is None:
+            _oracle_prepare((self.seeds, reference_schedule))
+        else:
+            for r in [p.apply_async(_oracle_prepare, ((self.seeds, reference_schedule),)) for p in self.pools]:
+                r.get()
+        self.ready.add(reference_schedule)
+
+    def step(self, reference_schedule):
+        """one timed step; returns (Newton iterations, wall seconds, busy seconds summed over the workers)"""
+        self.prepare(reference_schedule)
+        _NEXT.value = 0
+        t0 = time.perf_counter()
+        if self.pools is None:
+            res = [_oracle_solve_tickets(reference_schedule)]
+        else:
+            res = [r.get() for r in [p.apply_async(_oracle_solve_tickets, (reference_schedule,)) for p in self.pools]]
+        wall = time.perf_counter() - t0
+        assert sum(r[1] for r in res) == self.instances
+        return sum(r[0] for r in res), wall, sum(r[2] for r in res)
+
+    def close(self):
+        if self.pools:
+            for p in self.pools:
+                p.terminate()
+
+
+def oracle_kkt_solve_ms(seed=0):
     """One numeric factorisation + one solve of the reduced system on one core (the 'KKT solve' unit)."""
     from oracle import oracle as orc
-    P = lqc.cfg3(seed - 3000)
+    P = lqc.cfg3(seed)
     o = orc.from_problem(P)
     o.initialize(P.x0)
     o.solve_begin()
@@ -108,26 +163,36 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_step = max(cores, 8)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    instances = 4 * cores
+    pool = OraclePool(cores, instances)
+    pool.prepare(1)
     vals = []
     for step in range(args.warmup + args.steps):
-        seeds = list(range(step * per_step, (step + 1) * per_step))
-        v, iters, solves, wall = oracle_throughput(cores, seeds, 1, 60.0)
+        iters, wall, busy = pool.step(1)
         if step >= args.warmup:
-            vals.append((v, wall))
-    value = float(np.mean([v for v, _ in vals]))
-    ms = 1e3 * float(np.mean([w for _, w in vals]))
-    sample = f"{per_step} complete solve! runs of cfg3 per step on {cores} processes (one instance per process at a time), reference schedule (>=3 factorisations per Newton step)"
+            vals.append((iters / wall, wall, iters, busy))
+    dedup_iters, dedup_wall, _ = pool.step(0)
+    pool.close()
+    value = float(np.mean([v[0] for v in vals]))
+    ms = 1e3 * float(np.mean([v[1] for v in vals]))
+    it_step = float(np.mean([v[2] for v in vals]))
+    busy = float(np.mean([v[3] for v in vals]))
+    sample = (f"{instances} complete solve! runs of cfg3 per step (seeds 0..{instances - 1}) handed out one at a time to {cores} "
+              f"persistent processes; instance generation, ordering and symbolic analysis outside the timed region; reference "
+              f"schedule (>=3 factorisations per Newton step, as src/solver does)")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic",
-                config=dict(workload="cfg3 LQC(T=40,n_x=36,n_u=12,n_soc=100) N=4584 total=8496, complete solve! per instance",
-                            instances_per_step=per_step),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                data="synthetic", config=workload_config(args.batch, min(args.batch, args.distinct or args.batch), args.check_every),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
+                                  newton_iterations_per_step=it_step,
+                                  per_core_value_while_all_cores_run=it_step / busy,
+                                  scheduling_efficiency=busy / (cores * ms * 1e-3),
+                                  deduplicated_schedule_value=dedup_iters / dedup_wall),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                note="CPU oracle = C restatement of the reference algorithm (the Julia reference cannot run here; "
-                     "ordering and LU fallback are stand-ins, see oracle/oracle.h)")
+                note="CPU oracle = C restatement of the reference algorithm (the Julia reference cannot run here; the AMD "
+                     "ordering and the LU fallback are restated / stand-ins, see oracle/oracle.h); a step is a bounded sample "
+                     "of the GPU arm's workload (same instance family, fewer instances)")
     print(json.dumps(line))
 
 
@@ -175,6 +240,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from calipso_b200 import _lib
+    from calipso_b200.sharding import shard_range
     from calipso_b200.solver import BatchKKT
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,9 +265,9 @@ def run_gpu(args):
             os.dup2(saved_stdout0, 1)
             os.close(saved_stdout0)
     B = args.batch
-    distinct = min(B, args.distinct)
-    # instances: `distinct` different seeds per rank, tiled over the batch (values differ per seed, pattern shared)
-    Ps = make_instances(distinct, first_seed=rank * distinct)
+    distinct = min(B, args.distinct or B)
+    # instances: `distinct` different seeds per rank (by default all of the batch), values differ per seed, pattern shared
+    Ps = [lqc.cfg3(rank * distinct + i) for i in range(distinct)]
     plist = [Ps[i % distinct] for i in range(B)]
     k = BatchKKT(Ps[0], batch=B, device=local)
     info = k.info()
@@ -222,7 +288,8 @@ def run_gpu(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-    stream = torch.cuda.ExternalStream(k.lib.cb200_stream(k.h), device=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.ExternalStream(k.lib.cb200_stream(k.h), device=dev)
 
     def barrier():
         k.synchronize()
@@ -230,21 +297,38 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
 
-    def timed(fn, reps):
-        """device time of `reps` calls of fn on the handle's stream (ms per call), max over ranks"""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            fn()
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1) / reps
+    def rank_max(ms):
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
+
+    def rank_all(v):
+        if world == 1:
+            return [float(v)]
+        t = torch.zeros(world, device="cuda", dtype=torch.float64)
+        t[rank] = v
+        dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
+
+    def rank_sum(v):
+        if world > 1:
+            t = torch.tensor([v], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t)
+            v = int(t.item())
+        return int(v)
+
+    def timed(fn, reps, st=stream):
+        """device time of `reps` calls of fn on stream st (ms per call), max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            fn()
+        e1.record(st)
+        barrier()
+        return rank_max(e0.elapsed_time(e1) / reps)
 
     launches = [0, 0]              # all kernels of this library, k_lq_step launches
     lq_ms = [0.0]
@@ -268,12 +352,7 @@ def run_gpu(args):
         r = one_solve()
     st = k.stats()
     iters_per_solve = int((st["total_iterations"] - 1).sum())
-    if world > 1:
-        t = torch.tensor([iters_per_solve], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
-        total_iters = int(t.item())
-    else:
-        total_iters = iters_per_solve
+    total_iters = rank_sum(iters_per_solve)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -286,10 +365,28 @@ def run_gpu(args):
     gpu_launches = launches[0]
     conv = k.allreduce_counts()
     stats = {kk: v for kk, v in k.stats().items()}
+    fallbacks_per_solve = int((stats["fallbacks"] - st0["fallbacks"]).sum()) / max(args.steps, 1)
+    unrefined = int((stats["unrefined_steps"] - st0["unrefined_steps"]).sum())
+    it_hist = np.bincount(stats["total_iterations"] - 1)
+    per_rank_ms = rank_all(lq_ms[0] / max(launches[1], 1))
+    per_rank_iters = rank_all(iters_per_solve)
+    per_rank_max_iters = rank_all(int((stats["total_iterations"] - 1).max()))
 
-    # ---- dominant kernel of the step: k_lq_step (one Newton iteration of every running instance per launch).
-    # Algorithmic bytes = SURVEY.md section 8(d): per instance B_newton = B_res + B_cone + n_trials (B_asm + B_factor)
-    # + (1 + n_refine) (B_solve + B_spmv), with the factorisation / solve counts the kernel actually performed.
+    # ---- the same step with a scheduling hint: instances started in the order of decreasing iteration counts of the previous
+    # solve (cb200_lq_set_order; what a warm-started MPC loop would do).  Same results, fuller last wave; reported apart.
+    launches_keep, lq_keep = list(launches), lq_ms[0]
+    k.lq_set_order(np.argsort(-(stats["total_iterations"] - 1), kind="stable"))
+    one_solve()
+    ms_hint = timed(one_solve, max(2, args.steps // 2))
+    k.lq_set_order(None)
+    hint = dict(value=total_iters / (ms_hint * 1e-3), ms_per_step=ms_hint,
+                what="instances started longest-first by the previous solve's iteration counts (cb200_lq_set_order); results identical")
+    launches[:] = launches_keep
+    lq_ms[0] = lq_keep
+
+    # ---- dominant kernel of the step: k_lq_step.  Algorithmic bytes = SURVEY.md section 8(d): per instance B_newton = B_res +
+    # B_cone + n_trials (B_asm + B_factor) + (1 + n_refine) (B_solve + B_spmv), with the factorisation / solve counts the
+    # kernel actually performed.
     P0 = Ps[0]
     nW, nG, nC = len(P0.W_rowval), len(P0.G_rowval), len(P0.C_rowval)
     N_, T_, nK, nL = info["N"], info["total"], info["nnzK"], info["nnzL"]
@@ -304,7 +401,7 @@ def run_gpu(args):
     newton_bytes = d_fact * (b_asm + b_factor) + d_solv * (b_solve + b_spmv) + args.steps * iters_per_solve * (b_res + b_cone)
     n_lq_launches = launches[1]
     ms_lq_launch = lq_ms[0] / max(n_lq_launches, 1)
-    # ---- dominant kernel: KKT factor + solve (assemble + LDL^T + one reduced solve with recovery), roofline vs HBM
+    # ---- the KKT-solve unit: assemble + LDL^T + one reduced solve with recovery (k_kkt_factor_solve), roofline vs HBM
     k.lq_begin()
     k.lq_step(4)                   # realistic interior point
     k.set_scalars(eps_p=1e-7, eps_d=1e-7)
@@ -324,19 +421,24 @@ def run_gpu(args):
         if measured > 0.0:
             peak, peak_src = measured, "of measured: MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"
     kkt_achieved = b_unit * B / (ms_kkt * 1e-3) / 1e9
-    tpath2 = os.path.join(ROOT, "profiles", "lq_step_traffic.json")
-    # measured DRAM bytes of one Newton iteration of one instance (ncu capture of a launch in which every instance ran
-    # exactly one iteration), scaled to the Newton iterations an average launch of the timed region carried
-    traffic = None
-    if os.path.exists(tpath2):
-        per_it = json.load(open(tpath2)).get("dram_bytes_per_instance_iteration")
-        if per_it:
-            traffic = per_it * args.steps * iters_per_solve / max(n_lq_launches, 1)
-    tpath = os.path.join(ROOT, "profiles", "kkt_factor_solve_traffic.json")
-    kkt_traffic = json.load(open(tpath)).get("dram_bytes_per_instance") * B if os.path.exists(tpath) else None   # capture at batch 444, scaled
+
+    def traffic_of(fname, key):
+        path = os.path.join(ROOT, "profiles", fname)
+        try:
+            return json.load(open(path)).get(key)
+        except (OSError, ValueError):
+            return None
+    # measured DRAM bytes of one Newton iteration of one instance (ncu capture of a launch in which every instance ran exactly
+    # one iteration), scaled to the Newton iterations an average launch of the timed region carried
+    per_it = traffic_of("lq_step_traffic.json", "dram_bytes_per_instance_iteration")
+    traffic = per_it * args.steps * iters_per_solve / max(n_lq_launches, 1) if per_it else None
+    per_inst = traffic_of("kkt_factor_solve_traffic.json", "dram_bytes_per_instance")
+    kkt_traffic = per_inst * B if per_inst else None
     achieved = newton_bytes / max(n_lq_launches, 1) / (ms_lq_launch * 1e-3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     kernel="k_lq_step", launches_in_timed_region=n_lq_launches, ms_per_launch=ms_lq_launch,
+                    ms_per_launch_by_rank=per_rank_ms, newton_iterations_by_rank=per_rank_iters,
+                    longest_instance_by_rank=per_rank_max_iters,
                     algorithmic_bytes_per_launch=newton_bytes / max(n_lq_launches, 1),
                     algorithmic_bytes_formula="SURVEY 8(d): n_fact*(B_asm+B_factor) + n_solves*(B_solve+B_spmv) + n_newton*(B_res+B_cone)",
                     factorizations=d_fact, reduced_solves=d_solv, peak_source=peak_src,
@@ -358,126 +460,129 @@ def run_gpu(args):
                                                            "recovery: B_solve = 24 nnz(L) + 24 N"),
                                    what="assemble + LDL' factor + 1 reduced solve with recovery per instance: the 'KKT solve' "
                                         "unit of SURVEY 8(d), B_unit = 12 nnz(K) + 36 nnz(L) + 40 N"))
-    # ---- e2e: the reference-facing hot path through the C ABI with HOST buffers (pinned), copies inside the timing
-    k.lq_begin()
-    k.lq_step(4)
-    k.lq_evaluate(2 | 16 | 32)
-    k.cone(barrier=True, barrier_gradient=True, product=True)
-    names_in = ["POINT", "DUAL", "SCALARS", "GRADIENT", "EQ_DUAL_GRAD", "CONE_DUAL_GRAD", "EQUALITY", "CONE", "W_VALUES",
-                "G_VALUES", "C_VALUES"]
-    names_out = ["STEP", "CANDIDATE", "SCALARS"]
+
+    # ---- e2e: complete solve! of every instance through the C ABI from pinned HOST buffers.  Per step and instance: H2D of
+    # the problem data (W, G, C values, q, g0, h0 -- what evaluate! produces for this family) and of the guess, initialize!,
+    # solve! on the device, D2H of the solution point and of the statistics.  The batch is split over a few handles (one
+    # stream each) so that the copies of one chunk overlap the kernels of the others.
+    lib, A = k.lib, _lib.A
+    nchunks = max(1, min(args.e2e_chunks, B // 150 if B >= 300 else 1))       # chunks stay above one CTA per SM
+    bounds = [shard_range(B, c, nchunks) for c in range(nchunks)]
+    chunk_handles = [BatchKKT(Ps[0], batch=e - b, device=local) for b, e in bounds]
+    chunk_streams = [torch.cuda.ExternalStream(kc.lib.cb200_stream(kc.h), device=dev) for kc in chunk_handles]
+    data_names = (("W_VALUES", "W_val"), ("G_VALUES", "G_val"), ("C_VALUES", "C_val"), ("LQ_Q", "q"), ("LQ_G0", "g0"), ("LQ_H0", "h0"))
     host_in = {}
-    for nm in names_in:
-        a = k.get(nm)
+    for nm, attr in data_names:
+        a = np.stack([np.asarray(getattr(P, attr), dtype=np.float64) for P in plist])
         t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
         t.numpy()[...] = a
         host_in[nm] = t
-    host_out = {nm: torch.empty((B, k.length(nm)), dtype=torch.float64).pin_memory() for nm in names_out}
+    host_x0 = torch.empty(X0.shape, dtype=torch.float64).pin_memory()
+    host_x0.numpy()[...] = X0
+    host_w = torch.empty((B, info["total"]), dtype=torch.float64).pin_memory()
     stats_out = torch.empty((B, _lib.I_COUNT), dtype=torch.int32).pin_memory()
-    h2d = sum(t.numel() * 8 for t in host_in.values())
-    d2h = sum(t.numel() * 8 for t in host_out.values()) + stats_out.numel() * 4
-    lib, A = k.lib, _lib.A
-    # the batch is split over a few handles (each with its own stream) so that the H2D copies of one chunk overlap the
-    # kernels and the D2H copies of the others; every chunk does the complete upload -> hot path -> read-back
-    from calipso_b200.sharding import shard_range
-    nchunks = max(1, min(args.e2e_chunks, B))
-    bounds = [shard_range(B, c, nchunks) for c in range(nchunks)]
-    chunk_handles = [BatchKKT(Ps[0], batch=e - b, device=local) for b, e in bounds]
+    h2d = sum(t.numel() * 8 for t in host_in.values()) + host_x0.numel() * 8
+    d2h = host_w.numel() * 8 + stats_out.numel() * 4
 
     def at(t, b0, ctype):
         return _lib.C.cast(t.data_ptr() + b0 * t.shape[1] * t.element_size(), ctype)
 
+    e2e_ev = [torch.cuda.Event(enable_timing=True) for _ in range(nchunks + 1)]
+
     def e2e_step():
-        for (b0, e0_), kc in zip(bounds, chunk_handles):
+        e2e_ev[0].record(chunk_streams[0])
+        for c, ((b0, e0_), kc) in enumerate(zip(bounds, chunk_handles)):
             n_, hc = e0_ - b0, kc.h
             for nm, t in host_in.items():
                 lib.cb200_set_array(hc, A[nm], at(t, b0, _lib.c_dp), 0, n_)
-            lib.cb200_cone(hc, 7, 0)
-            lib.cb200_residual(hc)
-            lib.cb200_search_direction(hc)
-            lib.cb200_cone_search(hc)
-            for nm, t in host_out.items():
-                lib.cb200_get_array_async(hc, A[nm], at(t, b0, _lib.c_dp), 0, n_)
+            lib.cb200_initialize(hc, at(host_x0, b0, _lib.c_dp), 0, n_)
+            lib.cb200_lq_begin(hc, 0)
+            lib.cb200_lq_step(hc, args.max_newton)                  # one launch: every instance iterates to convergence
+            lib.cb200_get_array_async(hc, A["POINT"], at(host_w, b0, _lib.c_dp), 0, n_)
             lib.cb200_get_stats_async(hc, at(stats_out, b0, _lib.c_ip), 0, n_)
+            e2e_ev[c + 1].record(chunk_streams[c])
         for kc in chunk_handles:
             lib.cb200_synchronize(kc.h)
+        return max(e2e_ev[0].elapsed_time(e) for e in e2e_ev[1:])
 
     for _ in range(2):
         e2e_step()
-    assert int(stats_out[:, _lib.I["status"]].abs().sum()) == 0, "e2e step reported solver errors"
-    ms_e2e = timed(e2e_step, max(3, args.steps))
-    e2e_value = B * world / (ms_e2e * 1e-3)
-    e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e,
-               handles_per_gpu=nchunks,
-               what="one Newton step per instance through the C ABI from pinned host buffers: H2D of evaluate!'s outputs + "
-                    "point, cone!, residual!, search_direction!, cone search, D2H of step/candidate/scalars/stats; the batch "
-                    "is split over handles_per_gpu handles (one stream each) so copies overlap kernels")
+    assert int((stats_out[:, _lib.I["converged"]] != 1).sum()) == 0, "e2e: not every instance converged"
+    e2e_iters = rank_sum(int((stats_out[:, _lib.I["total_iterations"]] - 1).sum()))
+    barrier()
+    reps = max(3, args.steps)
+    ms_e2e = rank_max(sum(e2e_step() for _ in range(reps)) / reps)
+    barrier()
+    e2e = dict(value=e2e_iters / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e,
+               newton_iterations_per_step=e2e_iters, handles_per_gpu=nchunks,
+               what="complete solve! of every instance through the C ABI from pinned host buffers, per step: H2D of the problem "
+                    "data (W/G/C values, q, g0, h0) and of the guesses, initialize!, solve! (k_lq_begin + one k_lq_step launch "
+                    "per handle), D2H of the solution points and statistics; the batch is split over handles_per_gpu handles "
+                    "(one stream each) so copies overlap kernels; device time from the first H2D to the last D2H, max over ranks")
     for kc in chunk_handles:
         kc.close()
 
-    extras = {}
-    if rank == 0 and world == 1 and not args.no_single:
-        # cfg3 literal: ONE instance on one B200 (latency-bound), and cfg4 literal: 8 instances per GPU
-        for bb, key in ((1, "cfg3_single_instance"), (8, "cfg4_8_instances_per_gpu")):
-            kk = BatchKKT(Ps[0], batch=bb, device=local)
-            kk.load_lq([Ps[i % distinct] for i in range(bb)])
-            x0 = np.stack([Ps[i % distinct].x0 for i in range(bb)])
-            st2 = torch.cuda.ExternalStream(kk.lib.cb200_stream(kk.h), device=torch.device("cuda", local))
+    # ---- BASELINE.json's literal configurations, at every N: configs[4] = 8 instances per GPU (64 per box at 8 GPUs), and
+    # (rank 0) configs[3] = ONE instance on one B200
+    literal = {}
 
-            def solve2():
-                kk.initialize(x0)
-                kk.lq_begin()
-                kk.lq_solve(max_steps=args.max_newton, check_every=args.check_every)
-            for _ in range(2):
-                solve2()
-            kk.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st2)
-            for _ in range(3):
-                solve2()
-            e1.record(st2)
-            kk.synchronize()
-            ms = e0.elapsed_time(e1) / 3
-            its = int((kk.stats()["total_iterations"] - 1).sum())
+    def small_batch(bb, first_seed):
+        Pl = [lqc.cfg3(first_seed + i) for i in range(bb)]
+        kk = BatchKKT(Pl[0], batch=bb, device=local)
+        kk.load_lq(Pl)
+        x0 = np.stack([P.x0 for P in Pl])
+        st2 = torch.cuda.ExternalStream(kk.lib.cb200_stream(kk.h), device=dev)
+
+        def solve2():
+            kk.initialize(x0)
             kk.lq_begin()
-            kk.lq_step(4)
-            kk.set_scalars(eps_p=1e-7, eps_d=1e-7)
-            kk.kkt_factor_solve(1)
-            kk.synchronize()
-            e0.record(st2)
-            for _ in range(10):
-                kk.kkt_factor_solve(1)
-            e1.record(st2)
-            kk.synchronize()
-            extras[key] = dict(batch=bb, newton_it_per_s=its / (ms * 1e-3), ms_per_solve=ms, newton_iterations=its,
-                               kkt_factor_solve_ms=e0.elapsed_time(e1) / 10)
-            kk.close()
+            kk.lq_solve(max_steps=args.max_newton, check_every=args.check_every)
+        for _ in range(2):
+            solve2()
+        its = int((kk.stats()["total_iterations"] - 1).sum())
+        ms = timed(solve2, 3, st2)
+        kk.lq_begin()
+        kk.lq_step(4)
+        kk.set_scalars(eps_p=1e-7, eps_d=1e-7)
+        kk.kkt_factor_solve(1)
+        ms_unit = timed(lambda: kk.kkt_factor_solve(1), 10, st2)
+        kk.close()
+        return its, ms, ms_unit
+
+    if not args.no_literal:
+        its8, ms8, unit8 = small_batch(8, 8 * rank)                    # seeds 0..63 over 8 ranks: BASELINE configs[4]
+        tot8 = rank_sum(its8)
+        literal["cfg4_8_instances_per_gpu"] = dict(instances_per_gpu=8, instances=8 * world, newton_it_per_s=tot8 / (ms8 * 1e-3),
+                                                   ms_per_solve=ms8, newton_iterations=tot8, kkt_factor_solve_ms=unit8,
+                                                   what="BASELINE.json configs[4]: seeds 8*rank .. 8*rank+7 per GPU, max over ranks")
+        # configs[3]: one instance; every rank runs it (the timing helper contains collectives), rank 0's number is reported
+        its1, ms1, unit1 = small_batch(1, 0)
+        literal["cfg3_single_instance"] = dict(batch=1, newton_it_per_s=its1 / (ms1 * 1e-3), ms_per_solve=ms1,
+                                               newton_iterations=its1, kkt_factor_solve_ms=unit1,
+                                               what="BASELINE.json configs[3]: one instance on one B200 (one CTA: latency-bound)")
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, iters, solves, wall = oracle_throughput(1, list(range(64)), 1, args.cpu_budget)
-            v2, iters2, solves2, wall2 = oracle_throughput(1, list(range(64)), 0, args.cpu_budget / 2)
-            cpu = dict(value=v, unit=UNIT, cores=1, kind="port",
-                       sample=f"{solves} complete solve! runs of cfg3 (seeds 0..{solves - 1}), {iters} Newton iterations, "
-                              f"{wall:.1f} s on 1 core, reference schedule (>=3 factorisations per step)",
-                       deduplicated_schedule_value=v2, kkt_factor_solve_ms=oracle_kkt_solve_ms())
+            per = 6
+            pool = OraclePool(1, per)
+            pool.step(1)                                   # warm (also prepares: generation + symbolic, untimed)
+            it_r, w_r, _ = pool.step(1)
+            it_d, w_d, _ = pool.step(0)
+            cpu = dict(value=it_r / w_r, unit=UNIT, cores=1, kind="port",
+                       sample=f"{per} complete solve! runs of cfg3 (seeds 0..{per - 1}), {it_r} Newton iterations, {w_r:.1f} s on 1 core, "
+                              f"reference schedule (>=3 factorisations per step); set-up outside the timed region",
+                       deduplicated_schedule_value=it_d / w_d, kkt_factor_solve_ms=oracle_kkt_solve_ms())
+        cfg = workload_config(B, distinct, args.check_every)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                    data="synthetic",
-                    config=dict(workload=f"cfg4-style batch of cfg3 LQC(T=40,n_x=36,n_u=12,n_soc=100) instances, "
-                                         f"{B} per GPU, one complete solve! of every instance per step",
-                                N=info["N"], total=info["total"], n=info["n"], m=info["m"], p=info["p"],
-                                nnz_K_upper=info["nnzK"], nnz_L=info["nnzL"], supernodes=info["supernodes"],
-                                levels=info["levels"], batch_per_gpu=B, distinct_seeds_per_gpu=distinct,
-                                newton_iterations_per_step=total_iters,
-                                newton_iterations_per_launch_max=args.check_every,
-                                schedule="lock-step (one launch per Newton iteration)" if LOCKSTEP else
-                                         "independent (a launch carries up to check_every iterations of an instance)",
-                                l2_policy="inputs larger than L2: per-GPU working set = batch x ~4.5 MB",
-                                parallelism=f"instances sharded {B}/GPU, NCCL all-reduce of convergence counts only"),
+                    data="synthetic", config=cfg,
+                    symbolic=dict(nnz_K_upper=info["nnzK"], nnz_L=info["nnzL"], supernodes=info["supernodes"], levels=info["levels"],
+                                  ordering=os.environ.get("CB200_ORDERING", "mindeg")),
+                    newton_iterations_per_step=total_iters, with_schedule_hint=hint,
+                    iterations_histogram={int(i): int(c) for i, c in enumerate(it_hist) if c},
                     e2e=e2e, gpu_launches=gpu_launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks,
-                    converged=conv, fallbacks=int(stats["fallbacks"].sum()), **extras)
+                    converged=conv, fallbacks_per_solve=fallbacks_per_solve, unrefined_steps=unrefined, **literal)
         print(json.dumps(line))
     k.close()
     if world > 1:
@@ -490,15 +595,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1332, help="instances per GPU (9 per SM: three waves of 3 resident CTAs x 148 SMs)")
-    ap.add_argument("--distinct", type=int, default=64, help="distinct seeds per GPU, tiled over the batch")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct seeds per GPU, tiled over the batch (0: all distinct)")
     ap.add_argument("--max-newton", type=int, default=400)
     ap.add_argument("--check-every", type=int, default=400,
                     help="Newton iterations per k_lq_step launch / convergence check (default: run every instance to "
                          "convergence inside one launch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-single", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-literal", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="handles (streams) the e2e step pipelines the batch over")
     args = ap.parse_args()
     if args.impl == "reference":

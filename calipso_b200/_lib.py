@@ -109,6 +109,7 @@ SYMBOLS = {
     "cb200_lq_begin": (C.c_int, [vp, C.c_int]),
     "cb200_lq_step": (C.c_int, [vp, C.c_int]),
     "cb200_lq_solve": (C.c_int, [vp, C.c_int, C.c_int, c_llp, c_ip]),
+    "cb200_lq_set_order": (C.c_int, [vp, c_ip]),
     "cb200_ldl_factorize": (C.c_int, [vp]),
     "cb200_ldl_inertia": (C.c_int, [vp, c_ip]),
     "cb200_ldl_solve": (C.c_int, [vp]),

@@ -38,6 +38,7 @@ struct Batch {
     int *istat;
     long long *prof;
     int scratch_doubles;
+    const int *order;      // k_lq_step: CTA -> instance (null: identity); a scheduling hint, see cb200_lq_set_order
     __device__ __forceinline__ Inst inst(const DevProblem &P, int b) const
     {
         Inst I;
@@ -171,7 +172,10 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_begin(const __gr
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o, int iterations)
 {
-    KERNEL_PROLOGUE
+    CTX_SETUP
+    if ((int)blockIdx.x >= B.count) return;
+    const int b = B.order ? B.order[blockIdx.x] : (int)blockIdx.x;      // (CTAs are dispatched in blockIdx order)
+    Inst I = B.inst(P, b);
     // `iterations` Newton iterations of this instance inside one launch: instances are independent, so nothing forces
     // them into lock-step -- a CTA whose instance converges (or fails) leaves at once and the next instance of the batch
     // takes its place on the SM instead of waiting for the slowest instance of every iteration
@@ -308,6 +312,7 @@ struct cb200_handle {
     bool wide = false;          // heavy kernels with CB_THREADS_WIDE threads per instance (small batches)
     struct Scatter { ScatterPlan plan; const int *d_idx = nullptr; double *d_caches = nullptr; } scatter[3];   // W, G, C
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
+    int *d_order = nullptr;     // cb200_lq_set_order
 };
 
 extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
@@ -721,6 +726,28 @@ extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
     }
     return 0;
 }
+extern "C" int cb200_lq_set_order(cb200_handle *h, const int *order)
+{
+    NEED_KKT();
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (!order) { h->B.order = nullptr; return 0; }
+    std::vector<char> seen((size_t)h->batch, 0);
+    for (int i = 0; i < h->batch; i++) {
+        if (order[i] < 0 || order[i] >= h->batch || seen[(size_t)order[i]]) return fail("cb200_lq_set_order: not a permutation of the instances");
+        seen[(size_t)order[i]] = 1;
+    }
+    if (!h->d_order) {
+        void *d = nullptr;
+        CUDA_OK(cudaMalloc(&d, sizeof(int) * (size_t)h->batch));
+        h->allocs.push_back(d);
+        h->d_order = (int *)d;
+    }
+    CUDA_OK(cudaMemcpy(h->d_order, order, sizeof(int) * (size_t)h->batch, cudaMemcpyHostToDevice));
+    h->B.order = h->d_order;
+    return 0;
+}
+
 extern "C" int cb200_kkt_factor_solve(cb200_handle *h, int nsolves) { NEED_KKT(); FRESH_VALUES(); LAUNCH_SMEM(k_kkt_factor_solve, h->P, h->B, nsolves); return 0; }
 
 extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_host, double *S_host)

@@ -279,6 +279,12 @@ class BatchKKT:
     def lq_step(self, iterations=1):
         self.b.check(self.lib.cb200_lq_step(self.h, iterations))
 
+    def lq_set_order(self, order=None):
+        """Scheduling hint: start the instances in this order (a permutation of range(batch); None: identity).  Results do
+        not depend on it; `np.argsort(-previous_iteration_counts, kind="stable")` packs the tail of a batched re-solve."""
+        o = i32(order) if order is not None else None
+        self.b.check(self.lib.cb200_lq_set_order(self.h, ip(o) if o is not None else None))
+
     def lq_solve(self, max_steps=1100, check_every=4):
         counts = np.zeros(4, dtype=np.int64)
         steps = C.c_int(0)

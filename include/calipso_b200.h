@@ -224,6 +224,12 @@ int cb200_lq_begin(cb200_handle *h, int warmstart);                    /* solve.
  * failed) instance stops early and frees its place on the SM.  (CB200_LQ_LOCKSTEP=1 in the environment: one launch per
  * pass, all instances in lock-step -- bitwise the same results, for A/B timing.) */
 int cb200_lq_step(cb200_handle *h, int iterations);
+/* Scheduling hint for cb200_lq_step / cb200_lq_solve: the order in which the instances of the batch are started (order[k] =
+ * instance started k-th; a permutation of 0 .. batch-1; NULL restores the identity).  Instances are independent, so the
+ * order does not change any result; starting the instances that will need the most Newton iterations first (e.g. by the
+ * iteration counts of the previous solve in a warm-started MPC loop, examples/autotuning/cartpole.jl:146-226) packs the last
+ * wave of a batched solve. */
+int cb200_lq_set_order(cb200_handle *h, const int *order);
 /* run until every instance converged / gave up or max_steps passes; with an NCCL communicator attached the
  * termination test is the all-reduced count over ranks.  counts[4] = running, converged, gave up, error (global). */
 int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, long long *counts, int *steps_done);

@@ -384,6 +384,16 @@ extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
     for (int k = 0; k < iterations; k++) { FOR_EACH_INSTANCE solve_step_lq(ctx, P, I, h->opt); END_FOR }
     return 0;
 }
+extern "C" int cb200_lq_set_order(cb200_handle *h, const int *order)
+{   // a scheduling hint only: the emulation runs the instances one after the other in any case; the argument is validated
+    if (!order) return 0;
+    std::vector<char> seen((size_t)h->batch, 0);
+    for (int i = 0; i < h->batch; i++) {
+        if (order[i] < 0 || order[i] >= h->batch || seen[(size_t)order[i]]) { g_err = "cb200_lq_set_order: not a permutation of the instances"; return -1; }
+        seen[(size_t)order[i]] = 1;
+    }
+    return 0;
+}
 extern "C" int cb200_allreduce_counts(cb200_handle *h, long long *counts)
 {
     for (int k = 0; k < 4; k++) counts[k] = 0;

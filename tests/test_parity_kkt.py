@@ -68,8 +68,27 @@ def test_newton_step_pieces_cfg3(seed, iters):
     check_newton_step_pieces("cuda", lqc.cfg3(seed), iters)
 
 
-def check_newton_step_pieces(backend, P, iters):
-    k = BatchKKT(P, binding=backends.binding(backend))
+@pytest.mark.parametrize("backend", backends.BACKENDS)
+@pytest.mark.parametrize("make,iters", [(lqc.tiny, 3), (lqc.cfg2, 4)])
+def test_newton_step_pieces_in_the_reference_ordering(backend, make, iters):
+    """The same comparison with the reference's own elimination order, perm = amd(K) (qdldl.jl:135; restated ordering,
+    tests/test_amd.py), handed to the product through the perm argument of cb200_create."""
+    from test_amd import kkt_pattern
+    P = make()
+    K = kkt_pattern(P)
+    check_newton_step_pieces(backend, P, iters, perm=orc.amd(K.shape[0], K.indptr, K.indices))
+
+
+@pytest.mark.gpu
+def test_newton_step_pieces_cfg3_in_the_reference_ordering():
+    from test_amd import kkt_pattern
+    P = lqc.cfg3(1)
+    K = kkt_pattern(P)
+    check_newton_step_pieces("cuda", P, 3, perm=orc.amd(K.shape[0], K.indptr, K.indices))
+
+
+def check_newton_step_pieces(backend, P, iters, perm=None):
+    k = BatchKKT(P, perm=perm, binding=backends.binding(backend))
     perm, _, _ = k.symbolic()
     o = oracle_at_iteration(P, iters, perm=perm)
     # the oracle now performs one more iteration's worth of hot path, piece by piece

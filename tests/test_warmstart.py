@@ -39,3 +39,23 @@ def test_warmstarted_resolve_matches_oracle(backend):
     assert st["total_iterations"] == o2.stats["total_iterations"]
     assert np.abs(k.get("POINT")[0] - o2.solution).max() <= 1e-6 * max(1.0, np.abs(o2.solution).max())
     assert o2.stats["total_iterations"] <= cold_iterations + 2
+
+
+@pytest.mark.parametrize("backend", backends.BACKENDS)
+def test_schedule_hint_does_not_change_results(backend):
+    """cb200_lq_set_order: the order in which the instances of a batch are started (longest first in an MPC-style re-solve)
+    is a scheduling hint only -- every instance's iterates are bitwise those of the default order."""
+    Ps = [lqc.tiny(i) for i in range(7)]
+    k = BatchKKT(Ps[0], batch=7, binding=backends.binding(backend))
+    k.load_lq(Ps)
+    X0 = np.stack([P.x0 for P in Ps])
+    out = []
+    for order in (None, [3, 6, 0, 5, 1, 4, 2]):
+        k.lq_set_order(order)
+        k.initialize(X0)
+        k.lq_begin()
+        assert k.lq_solve(max_steps=300, check_every=300)["converged"] == 7
+        out.append((k.get("POINT"), k.stats()["total_iterations"].copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    with pytest.raises(Exception, match="permutation"):
+        k.lq_set_order([0, 0, 1, 2, 3, 4, 5])

@@ -1819,18 +1819,22 @@ CB_DEVN void recover_step(const Ctx &ctx, const DevProblem &P, const Inst &I, co
 
 // ------------------------------------------------------------------------------------------------ J * v (matrix-free)
 #if CB_ON_DEVICE
-// lane `sub` of a 4-lane group: sum over k = k0 + sub, k0 + sub + 4, ... < k1 of vals[src[k]] * vec[col[k]] (src == nullptr:
+#ifndef CB_JV_LANES
+#define CB_JV_LANES 4      // lanes per sparse row in J v (tunable: 4 or 8; measured in profiles/)
+#endif
+// lane `sub` of a G-lane group: sum over k = k0 + sub, k0 + sub + G, ... < k1 of vals[src[k]] * vec[col[k]] (src == nullptr:
 // vals[k]); eight entries per round with the index loads, then the value loads, batched
-__device__ __forceinline__ double sparse_dot4(const double *__restrict__ vals, const int *__restrict__ src,
-                                              const int *__restrict__ col, const double *vec, int k0, int k1, int sub)
+template <int G>
+__device__ __forceinline__ double sparse_dot(const double *__restrict__ vals, const int *__restrict__ src,
+                                             const int *__restrict__ col, const double *vec, int k0, int k1, int sub)
 {
     double acc = 0.0;
-    for (int q0 = k0 + sub; q0 < k1; q0 += 32) {
+    for (int q0 = k0 + sub; q0 < k1; q0 += 8 * G) {
         int si[8], ci[8];
         double vv[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int q = q0 + 4 * u;
+            const int q = q0 + G * u;
             const bool ok = q < k1;
             ci[u] = ok ? col[q] : 0;
             si[u] = ok ? (src ? src[q] : q) : -1;
@@ -1841,6 +1845,17 @@ __device__ __forceinline__ double sparse_dot4(const double *__restrict__ vals, c
         for (int u = 0; u < 8; u++) acc += vv[u] * vec[ci[u]];
     }
     return acc;
+}
+__device__ __forceinline__ double sparse_dot4(const double *__restrict__ vals, const int *__restrict__ src,
+                                              const int *__restrict__ col, const double *vec, int k0, int k1, int sub)
+{
+    return sparse_dot<4>(vals, src, col, vec, k0, k1, sub);
+}
+template <int G> __device__ __forceinline__ double group_sum(double a)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
 }
 #endif
 CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, const double *v, double *out)
@@ -1866,7 +1881,8 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
             for (int k = ctx.tid; k < m; k += ctx.nthr) sy[k] = vy[k];
             for (int k = ctx.tid; k < p; k += ctx.nthr) sz[k] = vz[k];
             __syncthreads();
-            const int sub = threadIdx.x & 3, gidx = threadIdx.x >> 2, ngrp = blockDim.x >> 2;
+            constexpr int JG = CB_JV_LANES;
+            const int sub = threadIdx.x & (JG - 1), gidx = threadIdx.x / JG, ngrp = blockDim.x / JG;
             {
                 const int padded = (n + ngrp - 1) / ngrp * ngrp;
                 int i = gidx;
@@ -1877,10 +1893,9 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
                     const bool okn = in < n;
                     const int nw0 = okn ? wp[in] : 0, nw1 = okn ? wp[in + 1] : 0, ng0 = okn ? gp[in] : 0,
                               ng1 = okn ? gp[in + 1] : 0, nc0 = okn ? cp[in] : 0, nc1 = okn ? cp[in + 1] : 0;
-                    double a = sparse_dot4(I.Wf, nullptr, wc, sx, w0, w1, sub) + sparse_dot4(Gv, nullptr, gi, sy, g0, g1, sub);
-                    for (int k = c0 + sub; k < c1; k += 4) a += Cv[k] * sz[ci[k]];
-                    a += __shfl_xor_sync(0xffffffffu, a, 1);
-                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    double a = sparse_dot<JG>(I.Wf, nullptr, wc, sx, w0, w1, sub) + sparse_dot<JG>(Gv, nullptr, gi, sy, g0, g1, sub);
+                    for (int k = c0 + sub; k < c1; k += JG) a += Cv[k] * sz[ci[k]];
+                    a = group_sum<JG>(a);
                     if (sub == 0 && i < n) out[i] = ep * sx[i] + a;
                     w0 = nw0; w1 = nw1; g0 = ng0; g1 = ng1; c0 = nc0; c1 = nc1;
                 }
@@ -1892,9 +1907,8 @@ CB_DEVN void jacobian_times(const Ctx &ctx, const DevProblem &P, const Inst &I, 
                 for (; i < padded; i += ngrp) {
                     const int in = i + ngrp;
                     const int na0 = in < m ? P.Grow.ptr[in] : 0, na1 = in < m ? P.Grow.ptr[in + 1] : 0;
-                    double a = sparse_dot4(I.Gr, nullptr, grc, sx, a0, a1, sub);
-                    a += __shfl_xor_sync(0xffffffffu, a, 1);
-                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    double a = sparse_dot<JG>(I.Gr, nullptr, grc, sx, a0, a1, sub);
+                    a = group_sum<JG>(a);
                     if (sub == 0 && i < m) {
                         out[n + i] = (rho + ep) * vr[i] - sy[i];
                         out[n + m + p + i] = a - vr[i] - ed * sy[i];

@@ -28,8 +28,24 @@ args = ap.parse_args()
 Ps = [lqc.cfg3(i) for i in range(args.distinct)]
 
 
+class LooseBinding(_lib.Binding):
+    """binding of an older build: symbols it does not export yet are skipped"""
+
+    def __init__(self, path):
+        import ctypes as C
+        self.path = path
+        self.lib = C.CDLL(path)
+        for name, (res, argtypes) in _lib.SYMBOLS.items():
+            try:
+                fn = getattr(self.lib, name)
+            except AttributeError:
+                continue
+            fn.restype = res
+            fn.argtypes = argtypes
+
+
 def make(path, B):
-    k = BatchKKT(Ps[0], batch=B, binding=_lib.Binding(path))
+    k = BatchKKT(Ps[0], batch=B, binding=LooseBinding(path))
     plist = [Ps[i % len(Ps)] for i in range(B)]
     k.load_lq(plist)
     k.X0 = np.stack([P.x0 for P in plist])

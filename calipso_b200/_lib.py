@@ -79,6 +79,7 @@ SYMBOLS = {
     "cb200_destroy": (None, [vp]),
     "cb200_info": (C.c_int, [vp, c_llp]),
     "cb200_amd_order": (C.c_int, [C.c_int, c_ip, c_ip, c_ip]),
+    "cb200_path_info": (C.c_int, [vp, c_llp]),
     "cb200_get_symbolic": (C.c_int, [vp, c_ip, c_ip, c_ip]),
     "cb200_get_factor": (C.c_int, [vp, C.c_int, c_ip, c_ip, c_dp, c_dp]),
     "cb200_set_array": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),

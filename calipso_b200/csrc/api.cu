@@ -389,7 +389,7 @@ static bool finish_batch(cb200_handle *h)
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        h->wide = h->batch <= sms;
+        h->wide = h->batch <= sms || h->sym().ctas_per_sm == 1;      // one CTA per SM anyway: give it 512 threads
         if (const char *e = getenv("CB200_THREADS")) h->wide = atoi(e) > CB_THREADS;   // testing / tuning override
     }
     h->B.scratch_doubles = h->sym().scratch_doubles;
@@ -474,7 +474,7 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     cb200_options dflt;
     cb200_options_default(&dflt);
     memcpy(&h->opt, &dflt, sizeof(Options));
-    const char *msg = h->gsym.analyze(N, Ap, Ai, perm, BIG_TASK_THRESHOLD);
+    const char *msg = h->gsym.analyze_auto(N, Ap, Ai, perm, BIG_TASK_THRESHOLD);
     if (msg[0]) { fail(msg); cb200_destroy(h); return nullptr; }
     DevProblem &P = h->P;
     bool ok = true;
@@ -521,6 +521,15 @@ extern "C" int cb200_info(const cb200_handle *h, long long *out)
     out[6] = (long long)S.phases.size(); out[7] = S.max_w; out[8] = S.max_nrow; out[9] = S.panel_total;
     out[10] = S.flops; out[11] = h->batch; out[12] = h->P.n; out[13] = h->P.m; out[14] = h->P.p;
     out[15] = (long long)h->nnzW + h->nnzG + h->nnzC;
+    return 0;
+}
+
+extern "C" int cb200_path_info(const cb200_handle *h, long long *out)
+{
+    const Symbolic &S = h->sym();
+    out[0] = S.solve_smem; out[1] = S.ctas_per_sm; out[2] = (long long)S.scratch_doubles * 8; out[3] = S.n_cta_tasks;
+    out[4] = S.n_generic_cta_tasks; out[5] = (long long)S.big.size() <= CB_MAX_CHAIN; out[6] = (long long)S.phases.size() <= CB_MAX_PHASES;
+    out[7] = h->wide ? CB_THREADS_WIDE : CB_THREADS;
     return 0;
 }
 

@@ -108,7 +108,7 @@ struct HostProblem {
             }
         }
         Kp[N] = (int)Ki.size();
-        const char *msg = sym.analyze(N, Kp.data(), Ki.data(), perm, big_threshold);
+        const char *msg = sym.analyze_auto(N, Kp.data(), Ki.data(), perm, big_threshold);
         if (msg[0]) return msg;
         // value codes of the fused assembly: array id << 30 | offset with arrays 0 = W values, 1 = G values,
         // 2 = C values, 3 = computed entries kx = [W diagonal + eps_p (n) | y diagonal (m) | nonnegative z diagonal (q_nn) |

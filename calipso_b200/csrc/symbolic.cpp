@@ -129,6 +129,22 @@ static void permuted_upper(int n, const int *Ap, const int *Ai, const std::vecto
         }
 }
 
+const char *Symbolic::analyze_auto(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold)
+{
+    // doubles of dynamic shared memory a CTA may plan with at 3 / 2 / 1 resident CTAs per SM: (233472 / c - 1 KB reserved
+    // - 4 KB static) / 8, the single-CTA figure capped by the 227 KB per-block limit
+    static const int budgets[3] = {9250, 13952, 28000};
+    const char *msg = "";
+    for (int k = 0; k < 3; k++) {
+        msg = analyze(n, Ap, Ai, user_perm, big_task_threshold, budgets[k]);
+        if (msg[0]) return msg;
+        ctas_per_sm = 3 - k;
+        smem_budget = budgets[k];
+        if (n_cta_tasks == 0 || (solve_smem && n_generic_cta_tasks == 0)) break;
+    }
+    return msg;
+}
+
 const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
                               int smem_budget_doubles)
 {
@@ -515,6 +531,10 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     }
     for (Phase &ph : phases) ph.first_big = ph.mode == 1 ? big_index[order[ph.begin]] : -1;
     big_seq_bwd.assign(big_seq.rbegin(), big_seq.rend());     // the backward solve visits them in exactly the reverse order
+    n_cta_tasks = n_generic_cta_tasks = 0;
+    for (const Phase &ph : phases)
+        if (ph.mode == 1)
+            for (int q = ph.begin; q < ph.end; q++) { n_cta_tasks++; n_generic_cta_tasks += big_index[order[q]] < 0; }
     {   // shared-memory solve: the permuted vector, two part buffers (TMA double buffering), one pivot window
         max_sb_doubles = (max_sb_doubles + 1) & ~1;
         int max_nR_big = 0;

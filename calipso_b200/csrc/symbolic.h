@@ -163,7 +163,14 @@ struct Symbolic {
     // still postordered (which does not change the fill) so that supernodes are contiguous.
     // Returns an empty string on success, else an error message.
     const char *analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
-                        int smem_budget_doubles = 9250);   // 74 KB + 2.6 KB static + 1 KB reserved, three CTAs per SM
+                        int smem_budget_doubles = 9250);   // 74 KB + 4 KB static + 1 KB reserved, three CTAs per SM
+    // The same with the shared-memory budget chosen for the pattern: the analysis is run for three, two and one resident
+    // CTA per SM (228 KB of shared memory per SM on sm_100) and the first plan that keeps the whole numeric path on the
+    // shared-memory code (solve with x[N] resident, every CTA-scope supernode staged) is kept; if none does, the last one.
+    const char *analyze_auto(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold);
+    int ctas_per_sm = 3;          // the occupancy the kept plan was sized for
+    int smem_budget = 9250;       // ... and its budget in doubles
+    int n_cta_tasks = 0, n_generic_cta_tasks = 0;   // CTA-scope supernodes / those that fell back to the global-memory code
 };
 
 // Default ordering: approximate minimum degree (amd.cpp) -- the published AMD algorithm with SuiteSparse's conventions and

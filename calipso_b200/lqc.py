@@ -186,3 +186,11 @@ def cfg3(instance: int = 0) -> ConicProblem:
 def tiny(instance: int = 0, T: int = 5, n_x: int = 4, n_u: int = 3, n_soc: int = 3) -> ConicProblem:
     """Small member of the family for fast tests."""
     return lqc(T, n_x, n_u, n_soc, 9000 + instance)
+
+
+def quadruped_shape(instance: int = 0) -> ConicProblem:
+    """An LQC instance with the dimensions of the reference's contact-implicit quadruped example
+    (test/examples/quadruped_gait.jl:236-244,460-464: reduced KKT dimension 6954, stage width 76): T = 36, n_x = 36,
+    n_u = 39, 100 SOC(3) cones -> N = 6987, stages of 75 variables.  Larger than BASELINE's cfg3 in N and wider than the
+    48-column supernode cap: exercises the shared-memory plans for two / one resident CTA per SM."""
+    return lqc(36, 36, 39, 100, 1000 * 5 + instance)

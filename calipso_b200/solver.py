@@ -165,6 +165,14 @@ class BatchKKT:
         self.lib.cb200_get_symbolic(self.h, ip(perm), ip(etree), ip(lnz))
         return perm, etree, lnz
 
+    def paths(self):
+        """Which code paths the pattern selected (cb200_path_info): speed, not results."""
+        out = np.zeros(8, dtype=np.int64)
+        self.lib.cb200_path_info(self.h, out.ctypes.data_as(_lib.c_llp))
+        keys = ("solve_in_shared_memory", "ctas_per_sm", "dynamic_smem_bytes", "cta_supernodes", "cta_supernodes_generic",
+                "chain_descriptors_cached", "schedule_cached", "threads_per_cta")
+        return dict(zip(keys, out.tolist()))
+
     def factor(self, instance=0):
         nnzL = self.info()["nnzL"]
         Lp, Li = np.zeros(self.N + 1, dtype=np.int32), np.zeros(nnzL, dtype=np.int32)

@@ -131,6 +131,13 @@ void cb200_destroy(cb200_handle *h); /* Julia finalizer */
 /* out[16]: N, total, nnz(K upper), nnz(L) (true fill), supernodes, levels, phases, max supernode width,
  * max panel rows, panel_total (doubles), sum Lnz^2, batch, n, m, p, nnz(W)+nnz(G)+nnz(C) */
 int cb200_info(const cb200_handle *h, long long *out);
+/* Which code paths the handle's pattern selected (they differ in speed, not in results).  out[8]: 1 if the solves keep
+ * x[N] in shared memory and stream the chain panels by TMA (else the global-memory solve); resident CTAs per SM the plan was
+ * sized for (3, 2 or 1: chosen from N and the widest supernode against the 228 KB of shared memory of an SM); dynamic
+ * shared memory per CTA in bytes; CTA-scope supernodes; those of them that do not fit the shared-memory staging and run
+ * the global-memory code; 1 if the chain descriptors / the phase schedule are cached in shared memory (<= 64 chain supernodes,
+ * <= 48 phases; otherwise they are read from global memory); threads per CTA of the heavy kernels (256 or 512). */
+int cb200_path_info(const cb200_handle *h, long long *out);
 /* amd(A) of src/solver/qdldl.jl:135 (AMD.jl / SuiteSparse AMD, default controls) for an N x N CSC pattern with sorted rows
  * (any triangle content; the ordering is that of A + A'): perm[k] = 0-based index eliminated k-th.  Host-only, no handle,
  * no GPU.  Pass the result as `perm` to cb200_create / cb200_ldl_create to factor in the reference's own elimination

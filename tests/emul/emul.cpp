@@ -133,7 +133,7 @@ extern "C" cb200_handle *cb200_ldl_create(int batch, int N, const int *Ap, const
     cb200_options d;
     cb200_options_default(&d);
     memcpy(&h->opt, &d, sizeof(Options));
-    const char *msg = h->gsym.analyze(N, Ap, Ai, perm, BIG_TASK_THRESHOLD);
+    const char *msg = h->gsym.analyze_auto(N, Ap, Ai, perm, BIG_TASK_THRESHOLD);
     if (msg[0]) { fail(msg); delete h; return nullptr; }
     fill_symbolic(h->P, h->gsym, [](const auto &v) { return v.data(); });
     h->P.nnzA = Ap[N];
@@ -159,6 +159,14 @@ extern "C" int cb200_info(const cb200_handle *h, long long *out)
     out[6] = (long long)S.phases.size(); out[7] = S.max_w; out[8] = S.max_nrow; out[9] = S.panel_total;
     out[10] = S.flops; out[11] = h->batch; out[12] = h->P.n; out[13] = h->P.m; out[14] = h->P.p;
     out[15] = (long long)h->P.nnzW + h->P.nnzG + h->P.nnzC;
+    return 0;
+}
+
+extern "C" int cb200_path_info(const cb200_handle *h, long long *out)
+{
+    const Symbolic &S = h->sym();
+    out[0] = S.solve_smem; out[1] = S.ctas_per_sm; out[2] = (long long)S.scratch_doubles * 8; out[3] = S.n_cta_tasks;
+    out[4] = S.n_generic_cta_tasks; out[5] = 1; out[6] = 1; out[7] = 1;      // (one emulated thread per instance)
     return 0;
 }
 

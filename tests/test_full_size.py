@@ -193,3 +193,20 @@ def test_narrow_and_wide_kernel_instantiations_agree():
     assert np.all(st["status"] == 0) and np.all(st["inertia_pos"] == Pc[0].n)
     e = kc.get("RESIDUAL") - kc.jacobian_times(kc.get("STEP"))
     assert np.abs(e).max() <= 1e-10
+
+
+def test_quadruped_shape_runs_on_the_shared_memory_path_and_matches_oracle():
+    """A pattern beyond BASELINE's cfg3 -- the dimensions of the reference's quadruped example (N = 6987, stages of 75
+    variables, test/examples/quadruped_gait.jl:236-244,460-464): the shared-memory plan is re-sized (two resident CTAs per
+    SM), nothing falls back to the global-memory code, and the complete solve! agrees with the oracle."""
+    Ps = [lqc.quadruped_shape(i) for i in range(3)]
+    k = BatchKKT(Ps[0], batch=3, binding=backends.binding("cuda"))
+    paths = k.paths()
+    assert paths["solve_in_shared_memory"] == 1 and paths["cta_supernodes_generic"] == 0 and paths["ctas_per_sm"] == 2
+    assert k.info()["N"] == 6987
+    k.load_lq(Ps)
+    k.initialize(np.stack([P.x0 for P in Ps]))
+    k.lq_begin()
+    r = k.lq_solve(max_steps=400, check_every=400)
+    assert r["converged"] == 3 and r["error"] == 0
+    _compare_batch_with_oracle(k, Ps)

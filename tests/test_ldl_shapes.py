@@ -90,3 +90,17 @@ def test_lq_conic_shapes_solve_like_the_oracle(backend, T, n_x, n_u, n_soc):
     st = {kk: int(v[0]) for kk, v in k.stats().items()}
     assert st["total_iterations"] == o.stats["total_iterations"]
     assert np.abs(k.get("POINT")[0] - o.solution).max() <= 1e-6 * max(1.0, np.abs(o.solution).max())
+
+
+def test_shared_memory_plan_follows_the_pattern():
+    """cb200_path_info: the shared-memory budget is chosen per pattern (three, two or one resident CTA per SM) so that the
+    solves keep x[N] in shared memory and every CTA-scope supernode is staged (host emulation: the plan is host-side)."""
+    from calipso_b200 import lqc
+    from calipso_b200.solver import BatchKKT
+    expect = {"tiny": 3, "cfg2": 3, "cfg3": 3, "quadruped_shape": 2}
+    for name, ctas in expect.items():
+        k = BatchKKT(getattr(lqc, name)(), binding=backends.binding("emul"))
+        p = k.paths()
+        assert p["solve_in_shared_memory"] == 1 and p["cta_supernodes_generic"] == 0, (name, p)
+        assert p["ctas_per_sm"] == ctas, (name, p)
+        assert p["dynamic_smem_bytes"] <= {3: 74000, 2: 111616, 1: 224000}[ctas]

@@ -27,7 +27,7 @@ A = {name: i for i, name in enumerate(ARRAYS)}
 SCALARS = ["kappa", "tau", "rho", "eps_p", "eps_d", "eps_p_last", "objective", "barrier", "residual_violation",
            "optimality_violation", "slack_violation", "theta", "merit", "step_size", "step_size_t",
            "equality_violation", "cone_product_violation", "refine_norm", "refine_norm_initial", "merit_candidate",
-           "theta_candidate"]
+           "theta_candidate", "merit_slope", "step_size_cone"]
 S = {name: i for i, name in enumerate(SCALARS)}
 S_COUNT = 24
 STATS = ["inertia_pos", "inertia_neg", "inertia_zero", "n_trials", "n_refine", "refine_ok", "k_s", "k_t", "status",
@@ -111,6 +111,8 @@ SYMBOLS = {
     "cb200_lq_step": (C.c_int, [vp, C.c_int]),
     "cb200_lq_solve": (C.c_int, [vp, C.c_int, C.c_int, c_llp, c_ip]),
     "cb200_lq_set_order": (C.c_int, [vp, c_ip]),
+    "cb200_filter_reset": (C.c_int, [vp]),
+    "cb200_filter_search": (C.c_int, [vp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_ip]),
     "cb200_ldl_factorize": (C.c_int, [vp]),
     "cb200_ldl_inertia": (C.c_int, [vp, c_ip]),
     "cb200_ldl_solve": (C.c_int, [vp]),

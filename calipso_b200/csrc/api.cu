@@ -151,6 +151,23 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_apply_step(const __
     (void)n;
 }
 
+// filter line search over uploaded candidates (solve.jl:224-306), see cb200_filter_search
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_filter_search(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o,
+                                                                            int first, int count, const double *fc, const double *gc,
+                                                                            const double *hc, int *accepted)
+{
+    KERNEL_PROLOGUE
+    const int a = filter_search(ctx, P, I, o, first, count, fc + (long long)b * count, gc + (long long)b * count * P.m,
+                                hc + (long long)b * count * P.p);
+    if (ctx.tid == 0) accepted[b] = a;
+}
+
+__global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_filter_reset(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+{
+    KERNEL_PROLOGUE
+    filter_reset(ctx, I, o);
+}
+
 __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_jtimes(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {   // tmp <- J * err  (err used as the input vector)
     KERNEL_PROLOGUE
@@ -313,6 +330,8 @@ struct cb200_handle {
     struct Scatter { ScatterPlan plan; const int *d_idx = nullptr; double *d_caches = nullptr; } scatter[3];   // W, G, C
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
     int *d_order = nullptr;     // cb200_lq_set_order
+    double *d_cand = nullptr;   // cb200_filter_search: candidates' callback outputs
+    size_t cand_bytes = 0;
 };
 
 extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
@@ -735,6 +754,42 @@ extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
     }
     return 0;
 }
+extern "C" int cb200_filter_reset(cb200_handle *h) { NEED_KKT(); LAUNCH(k_filter_reset, h->P, h->B, h->opt); return 0; }
+
+extern "C" int cb200_filter_search(cb200_handle *h, int first, int count, const double *f_host, const double *g_host,
+                                   const double *h_host, int *accepted_host)
+{
+    NEED_KKT();
+    if (first < 0 || count <= 0 || !f_host || !accepted_host) return fail("cb200_filter_search: invalid arguments");
+    CUDA_OK(cudaSetDevice(h->device));
+    const size_t B = (size_t)h->batch, m = (size_t)h->P.m, p = (size_t)h->P.p, c = (size_t)count;
+    const size_t nf = B * c, ng = B * c * m, nh = B * c * p;
+    const size_t need = (nf + ng + nh) * sizeof(double) + B * sizeof(int);
+    if (need > h->cand_bytes) {      // staging buffer of the candidates' callback outputs, grown on demand
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        if (h->d_cand) {
+            h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void *)h->d_cand), h->allocs.end());
+            cudaFree(h->d_cand);
+            h->d_cand = nullptr;
+            h->cand_bytes = 0;
+        }
+        void *d = nullptr;
+        CUDA_OK(cudaMalloc(&d, need));
+        h->allocs.push_back(d);
+        h->d_cand = (double *)d;
+        h->cand_bytes = need;
+    }
+    double *df = h->d_cand, *dg = df + nf, *dh = dg + ng;
+    int *dacc = (int *)(dh + nh);
+    CUDA_OK(cudaMemcpyAsync(df, f_host, nf * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (ng) CUDA_OK(cudaMemcpyAsync(dg, g_host, ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (nh) CUDA_OK(cudaMemcpyAsync(dh, h_host, nh * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_filter_search, h->P, h->B, h->opt, first, count, df, dg, dh, dacc);
+    CUDA_OK(cudaMemcpyAsync(accepted_host, dacc, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int cb200_lq_set_order(cb200_handle *h, const int *order)
 {
     NEED_KKT();

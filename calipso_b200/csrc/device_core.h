@@ -128,7 +128,7 @@ enum {
     S_KAPPA = 0, S_TAU, S_RHO, S_EPSP, S_EPSD, S_EPSP_LAST, S_OBJECTIVE, S_BARRIER,
     S_RESIDUAL_VIOLATION, S_OPTIMALITY_VIOLATION, S_SLACK_VIOLATION, S_THETA, S_MERIT,
     S_STEP_SIZE, S_STEP_SIZE_T, S_EQUALITY_VIOLATION, S_CONE_PRODUCT_VIOLATION,
-    S_REFINE_NORM, S_REFINE_NORM_INITIAL, S_MERIT_CANDIDATE, S_THETA_CANDIDATE, S_COUNT = 24
+    S_REFINE_NORM, S_REFINE_NORM_INITIAL, S_MERIT_CANDIDATE, S_THETA_CANDIDATE, S_MERIT_SLOPE, S_STEP_SIZE_CONE, S_COUNT = 24
 };
 enum {
     I_INERTIA_POS = 0, I_INERTIA_NEG, I_INERTIA_ZERO, I_TRIALS, I_REFINE, I_REFINE_OK, I_KS, I_KT, I_STATUS,

@@ -143,6 +143,74 @@ CB_DEV bool armijo(double M, double Mc, double d, double step_size, double at, d
     return Mc - M - 10.0 * mach * fabs(M) <= at * step_size * d;
 }
 
+// The residual (filter) line search of solve.jl:224-306 over candidates whose callback outputs were computed elsewhere:
+// fc[k], gc[k][m], hc[k][p] = f, g, h at w - alpha_k step, alpha_k = alpha_cone 0.5^(first + k).  Returns the index
+// (first + k) of the accepted candidate or -1.  Same tests, in the same order, as the on-device loop of
+// newton_iteration_lq below; state that spans calls (merit, theta, slope, alpha_cone) lives in the scalar slots.
+CB_DEVN int filter_search(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o, int first, int count,
+                          const double *fc, const double *gc, const double *hc)
+{
+    const int n = P.n, m = P.m, p = P.p, N = P.N;
+    const double *w = I.w;
+    double *c = I.cand;
+    if (first == 0) {
+        // current point: merit, merit gradient, slope, theta (solve.jl:141-150,170-172,231-233)
+        const double M0 = merit_value(ctx, P, I, w);
+        merit_gradient(ctx, P, I);
+        const double th0 = constraint_violation(ctx, P, I, w);
+        const double d0 = scope_sum(ctx, N, [&](int i) { return I.mgrad[i] * I.step[i]; });
+        if (ctx.tid == 0) {
+            I.scal[S_MERIT] = M0; I.scal[S_THETA] = th0; I.scal[S_MERIT_SLOPE] = d0; I.scal[S_STEP_SIZE_CONE] = I.scal[S_STEP_SIZE];
+        }
+        ctx.sync();
+    }
+    const double M = I.scal[S_MERIT], theta = I.scal[S_THETA], d = I.scal[S_MERIT_SLOPE], a0 = I.scal[S_STEP_SIZE_CONE];
+    const double f_keep = I.scal[S_OBJECTIVE], phi_keep = I.scal[S_BARRIER];
+    ctx.sync();
+    int accepted = -1;
+    double step_size = a0, Mh = 0.0, theta_h = 0.0;
+    for (int k = 0; k < first; k++) step_size = o.scaling_line_search * step_size;
+    for (int k = 0; k < count; k++) {
+        PAR_FOR(i, N) c[i] = w[i] - step_size * I.step[i];                      // x, r, s of the candidate (solve.jl:224-229,292-294)
+        PAR_FOR(i, m) I.g[i] = gc[(long long)k * m + i];
+        PAR_FOR(i, p) I.h[i] = hc[(long long)k * p + i];
+        if (ctx.tid == 0) I.scal[S_OBJECTIVE] = fc[k];
+        ctx.sync();
+        cone_eval(ctx, P, I, c, 1, 0, 0);
+        Mh = merit_value(ctx, P, I, c);
+        theta_h = constraint_violation(ctx, P, I, c);
+        bool ok = false;
+        if (check_filter(ctx, I, o, theta_h, Mh)) {
+            if (theta <= o.slack_tolerance && switching_condition(step_size, d, o.merit_exponent, theta, o.violation_exponent, 1.0) &&
+                armijo(M, Mh, d, step_size, o.armijo_tolerance, o.machine_tolerance))
+                ok = true;
+            else if (sufficient_progress(theta, theta_h, M, Mh, o.violation_tolerance, o.merit_tolerance, o.machine_tolerance))
+                ok = true;
+        }
+        // the reference leaves the loop after max_residual_line_search halvings with the last candidate evaluated
+        if (ok || first + k >= o.max_residual_line_search) { accepted = first + k; break; }
+        step_size = o.scaling_line_search * step_size;
+    }
+    ctx.sync();
+    if (accepted >= 0) {
+        // augment_filter!(solver, ...), filter.jl:81-89 / solve.jl:298-306
+        if (!switching_condition(step_size, d, o.merit_exponent, theta, o.violation_exponent, 1.0) ||
+            !armijo(M, Mh, d, step_size, o.armijo_tolerance, o.machine_tolerance))
+            augment_filter_pair(ctx, I, o, (1.0 - o.violation_tolerance) * theta, M - o.merit_tolerance * theta);
+        if (ctx.tid == 0) {
+            I.scal[S_STEP_SIZE] = step_size;
+            I.scal[S_MERIT_CANDIDATE] = Mh;
+            I.scal[S_THETA_CANDIDATE] = theta_h;
+            I.istat[I_LINE_SEARCH] = accepted;
+        }
+    } else if (ctx.tid == 0) {          // nothing accepted yet: the current point's objective and barrier stay in their slots
+        I.scal[S_OBJECTIVE] = f_keep;
+        I.scal[S_BARRIER] = phi_keep;
+    }
+    ctx.sync();
+    return accepted;
+}
+
 // ------------------------------------------------------------------------------------------------ solve! pieces
 // solve.jl:8-95
 CB_DEVN void solve_begin_lq(const Ctx &ctx, const DevProblem &P, const Inst &I, const Options &o, int warmstart)

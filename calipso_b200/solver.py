@@ -287,6 +287,21 @@ class BatchKKT:
     def lq_step(self, iterations=1):
         self.b.check(self.lib.cb200_lq_step(self.h, iterations))
 
+    def filter_reset(self):
+        """reset!(solver.filter), solve.jl:93,367 (the filter of cb200_filter_search lives on the device)"""
+        self.b.check(self.lib.cb200_filter_reset(self.h))
+
+    def filter_search(self, first, f, g, h):
+        """Filter line search over candidates first .. first+count-1 (solve.jl:224-306): f [batch, count], g [batch, count, m],
+        h [batch, count, p] = evaluate!'s outputs at w - alpha_cone 0.5^k step.  Returns the accepted index per instance or -1."""
+        f = f64(f).reshape(self.batch, -1)
+        count = f.shape[1]
+        g = f64(g).reshape(self.batch, count, self.m)
+        h = f64(h).reshape(self.batch, count, self.p)
+        acc = np.zeros(self.batch, dtype=np.int32)
+        self.b.check(self.lib.cb200_filter_search(self.h, first, count, dp(f), dp(g), dp(h), ip(acc)))
+        return acc
+
     def lq_set_order(self, order=None):
         """Scheduling hint: start the instances in this order (a permutation of range(batch); None: identity).  Results do
         not depend on it; `np.argsort(-previous_iteration_counts, kind="stable")` packs the tail of a batched re-solve."""
@@ -359,10 +374,12 @@ class Solver:
     One instance per Solver (batch = 1), like the reference.
     """
 
-    def __init__(self, problem, callback, options: Options | None = None, device: int = 0, perm=None, binding=None):
+    def __init__(self, problem, callback, options: Options | None = None, device: int = 0, perm=None, binding=None,
+                 line_search_on_device: bool = False):
         self.options = options or Options()
         self.problem = problem
         self.callback = callback
+        self.line_search_on_device = line_search_on_device   # filter line search through cb200_filter_search (SURVEY 8f N3)
         self.kkt = BatchKKT(problem, batch=1, perm=perm, options=self.options, device=device, binding=binding)
         k = self.kkt
         self.n, self.m, self.p, self.total = k.n, k.m, k.p, k.total
@@ -449,6 +466,8 @@ def solve(solver: Solver) -> bool:
     k.set("POINT", w)
     k.cone(product=True)
     s_.filter.reset()
+    if s_.line_search_on_device:
+        k.filter_reset()
     total_iterations = 1
     for j in range(1, opt.max_outer_iterations + 1):
         for i in range(1, opt.max_residual_iterations + 1):
@@ -496,6 +515,32 @@ def solve(solver: Solver) -> bool:
             step_size = sc["step_size"]
             step = k.get("STEP")[0]
             cand = k.get("CANDIDATE")[0]
+            if s_.line_search_on_device:
+                # the filter line search on the device: evaluate! at blocks of candidate step sizes (1, 2, 4, ... at a time),
+                # merit / violation / filter tests in cb200_filter_search; the host only runs the callbacks
+                k.set_scalars(objective=o.objective[0])
+                first, count, accepted = 0, 1, -1
+                while accepted < 0:
+                    fs, gs, hs = [], [], []
+                    for kk in range(first, first + count):
+                        xc = w[:n] - step_size * opt.scaling_line_search ** kk * step[:n]
+                        s_.callback(E.EV_OBJECTIVE | E.EV_EQUALITY | E.EV_CONE, xc, w[iy], w[iz], o)
+                        fs.append(o.objective[0]); gs.append(o.equality.copy()); hs.append(o.cone.copy())
+                    accepted = int(k.filter_search(first, np.array(fs)[None], np.array(gs)[None] if m else np.zeros((1, count, 0)),
+                                                   np.array(hs)[None] if p else np.zeros((1, count, 0)))[0])
+                    if accepted >= 0:
+                        o.objective[0] = fs[accepted - first]
+                        o.equality[:] = gs[accepted - first]
+                        o.cone[:] = hs[accepted - first]
+                    first, count = first + count, 2 * count
+                k.apply_step()
+                w[:] = k.get("POINT")[0]
+                sc = {kk: v[0] for kk, v in k.scalars().items()}
+                equality_violation = sc["equality_violation"]
+                cone_product_violation = sc["cone_product_violation"]
+                s_.log.append(dict(st, iteration=total_iterations, outer=j, inner=i, step_size=sc["step_size"]))
+                total_iterations += 1
+                continue
             s_.evaluate(E.EV_OBJECTIVE | E.EV_EQUALITY | E.EV_CONE, cand)
             M_hat = s_._merit(o.objective[0], cand[ir], s_._barrier(cand[isl]))
             theta_hat = s_._theta(o.equality, cand[ir], o.cone, cand[isl])
@@ -533,6 +578,8 @@ def solve(solver: Solver) -> bool:
         s_.dual[:] = s_.dual + s_.penalty * w[ir]
         s_.penalty = min(max(opt.penalty_scaling * s_.penalty, 1.0 / s_.central_path), opt.max_penalty)
         s_.filter.reset()
+        if s_.line_search_on_device:
+            k.filter_reset()
     s_.iterations = total_iterations
     return False
 

@@ -95,7 +95,7 @@ enum {
     CB200_S_BARRIER, CB200_S_RESIDUAL_VIOLATION, CB200_S_OPTIMALITY_VIOLATION, CB200_S_SLACK_VIOLATION,
     CB200_S_THETA, CB200_S_MERIT, CB200_S_STEP_SIZE, CB200_S_STEP_SIZE_T, CB200_S_EQUALITY_VIOLATION,
     CB200_S_CONE_PRODUCT_VIOLATION, CB200_S_REFINE_NORM, CB200_S_REFINE_NORM_INITIAL, CB200_S_MERIT_CANDIDATE,
-    CB200_S_THETA_CANDIDATE, CB200_S_COUNT = 24
+    CB200_S_THETA_CANDIDATE, CB200_S_MERIT_SLOPE, CB200_S_STEP_SIZE_CONE, CB200_S_COUNT = 24
 };
 /* integer slots returned by cb200_get_stats */
 enum {
@@ -231,6 +231,21 @@ int cb200_lq_begin(cb200_handle *h, int warmstart);                    /* solve.
  * failed) instance stops early and frees its place on the SM.  (CB200_LQ_LOCKSTEP=1 in the environment: one launch per
  * pass, all instances in lock-step -- bitwise the same results, for A/B timing.) */
 int cb200_lq_step(cb200_handle *h, int iterations);
+/* The filter line search of solve! (src/solver/solve.jl:224-306 with filter.jl:43-89 and line_search.jl:2-15) for callers
+ * whose callbacks run outside the library: the candidates are w - alpha_k * step, alpha_k = alpha_cone * 0.5^k, k = first ..
+ * first+count-1 (alpha_cone = the step size cb200_cone_search left), and the caller hands over what evaluate! returned at
+ * each of them -- objective f_host[batch][count], equality constraint g_host[batch][count][m], cone constraint
+ * h_host[batch][count][p] (host pointers).  Per instance the kernel forms the candidate slacks, barrier, merit and constraint
+ * violation of every candidate, walks them in order through the filter / switching / Armijo / sufficient-progress tests
+ * (first == 0 also computes merit, merit gradient and slope at the current point from CB200_GRADIENT, CB200_DUAL,
+ * CB200_EQUALITY, CB200_CONE, CB200_S_OBJECTIVE and the barrier of the last cb200_cone call) and stops at the first
+ * acceptable one: accepted_host[b] = its index k (then CB200_S_STEP_SIZE, _MERIT_CANDIDATE, _THETA_CANDIDATE and
+ * CB200_I_LINE_SEARCH are set, the filter is augmented as solve.jl:298-306 does, CB200_EQUALITY / CB200_CONE hold the
+ * accepted candidate's values and cb200_apply_step may follow) or -1 (call again with first += count).  The filter itself
+ * lives on the device; cb200_filter_reset empties it (solve.jl:93, :367). */
+int cb200_filter_reset(cb200_handle *h);
+int cb200_filter_search(cb200_handle *h, int first, int count, const double *f_host, const double *g_host, const double *h_host,
+                        int *accepted_host);
 /* Scheduling hint for cb200_lq_step / cb200_lq_solve: the order in which the instances of the batch are started (order[k] =
  * instance started k-th; a permutation of 0 .. batch-1; NULL restores the identity).  Instances are independent, so the
  * order does not change any result; starting the instances that will need the most Newton iterations first (e.g. by the

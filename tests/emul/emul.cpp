@@ -392,6 +392,21 @@ extern "C" int cb200_lq_step(cb200_handle *h, int iterations)
     for (int k = 0; k < iterations; k++) { FOR_EACH_INSTANCE solve_step_lq(ctx, P, I, h->opt); END_FOR }
     return 0;
 }
+extern "C" int cb200_filter_reset(cb200_handle *h)
+{
+    FOR_EACH_INSTANCE filter_reset(ctx, I, h->opt); END_FOR
+    return 0;
+}
+extern "C" int cb200_filter_search(cb200_handle *h, int first, int count, const double *f_host, const double *g_host,
+                                   const double *h_host, int *accepted_host)
+{
+    if (first < 0 || count <= 0 || !f_host || !accepted_host) return fail("cb200_filter_search: invalid arguments");
+    FOR_EACH_INSTANCE
+        accepted_host[b] = filter_search(ctx, P, I, h->opt, first, count, f_host + (long long)b * count,
+                                         g_host + (long long)b * count * P.m, h_host + (long long)b * count * P.p);
+    END_FOR
+    return 0;
+}
 extern "C" int cb200_lq_set_order(cb200_handle *h, const int *order)
 {   // a scheduling hint only: the emulation runs the instances one after the other in any case; the argument is validated
     if (!order) return 0;

@@ -229,13 +229,15 @@ def test_batch_of_instances_is_independent(backend):
 
 
 @pytest.mark.parametrize("backend", backends.BACKENDS)
+@pytest.mark.parametrize("device_line_search", [False, True])
 @pytest.mark.parametrize("name", ["wachter", "maratos", "knitro", "test1", "test2", "test3", "test4", "portfolio", "pendulum",
                                   "pendulum_overwrite", "qp_nonnegative"])
-def test_reference_solver_cases_through_host_callbacks(backend, name):
+def test_reference_solver_cases_through_host_callbacks(backend, name, device_line_search):
     """test/solver/*.jl cases through Solver / initialize! / solve! with host callbacks and the GPU hot path:
-    same stopping criteria (e.g. wachter.jl:36-45) and the oracle's solution."""
+    same stopping criteria (e.g. wachter.jl:36-45) and the oracle's solution.  device_line_search: the filter line search of
+    solve.jl:224-306 through cb200_filter_search (candidates' callback outputs uploaded in blocks) instead of host Python."""
     P = getattr(problems, name)()
-    s = Solver(P, P.callback, binding=backends.binding(backend))
+    s = Solver(P, P.callback, binding=backends.binding(backend), line_search_on_device=device_line_search)
     initialize(s, P.x0)
     assert solve(s) is True
     R = s.residual

@@ -561,6 +561,35 @@ def run_gpu(args):
                                                newton_iterations=its1, kkt_factor_solve_ms=unit1,
                                                what="BASELINE.json configs[3]: one instance on one B200 (one CTA: latency-bound)")
 
+    # ---- differentiate!: solution sensitivities of a few instances for many parameters -- one factorisation per
+    # instance, one CTA per (instance, parameter) column; through the C ABI with host buffers (copies inside the timing)
+    diff = None
+    if not args.no_literal:
+        nb, npar = 8, 64
+        Pd = [lqc.cfg3(8 * rank + i) for i in range(nb)]
+        kd = BatchKKT(Pd[0], batch=nb, device=local)
+        kd.load_lq(Pd)
+        kd.initialize(np.stack([P.x0 for P in Pd]))
+        kd.lq_begin()
+        kd.lq_solve(max_steps=args.max_newton, check_every=args.check_every)       # sensitivities are taken at the solution
+        Hd = torch.empty((nb * npar, info["total"]), dtype=torch.float64).pin_memory()      # one right-hand side per row
+        Hd.numpy()[...] = np.random.default_rng(rank).standard_normal(Hd.shape)
+        Sd = torch.empty_like(Hd).pin_memory()
+        std = torch.cuda.ExternalStream(kd.lib.cb200_stream(kd.h), device=dev)
+
+        def diff_call():
+            kd.b.check(kd.lib.cb200_differentiate(kd.h, npar, _lib.C.cast(Hd.data_ptr(), _lib.c_dp), _lib.C.cast(Sd.data_ptr(), _lib.c_dp)))
+        diff_call()
+        ms_d = timed(diff_call, 5, std)
+        cols = nb * npar * world
+        diff = dict(instances_per_gpu=nb, parameters=npar, ms_per_call=ms_d, sensitivity_columns_per_second=cols / (ms_d * 1e-3),
+                    algorithmic_bytes_per_gpu=nb * (b_asm + b_factor) + nb * npar * b_solve,
+                    achieved_gbs_incl_copies=(nb * (b_asm + b_factor) + nb * npar * b_solve) / (ms_d * 1e-3) / 1e9,
+                    h2d_bytes=Hd.numel() * 8, d2h_bytes=Sd.numel() * 8,
+                    what="cb200_differentiate on 8 converged cfg3 instances per GPU x 64 parameter columns (random dR/dtheta): H2D, "
+                         "assemble + factor once per instance, 512 reduced solves with recovery on 512 CTAs, D2H")
+        kd.close()
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -582,7 +611,7 @@ def run_gpu(args):
                     newton_iterations_per_step=total_iters, with_schedule_hint=hint,
                     iterations_histogram={int(i): int(c) for i, c in enumerate(it_hist) if c},
                     e2e=e2e, gpu_launches=gpu_launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks,
-                    converged=conv, fallbacks_per_solve=fallbacks_per_solve, unrefined_steps=unrefined, **literal)
+                    converged=conv, fallbacks_per_solve=fallbacks_per_solve, unrefined_steps=unrefined, differentiate=diff, **literal)
         print(json.dumps(line))
     k.close()
     if world > 1:

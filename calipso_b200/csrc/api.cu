@@ -247,22 +247,30 @@ __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS :
     PROF_FLUSH(I.prof);
 }
 
-// differentiate!: one factorisation, num_parameters reduced solves with recovery, sign flip (differentiate.jl:13-57)
+// differentiate!: one factorisation, num_parameters reduced solves with recovery, sign flip (differentiate.jl:13-57).  The
+// factorisation is k_kkt_factor_solve with nsolves = 0; the right-hand sides are independent, so every (instance,
+// parameter) pair gets its own CTA -- a single problem with many parameters fills the GPU instead of running its columns
+// one after the other on one SM -- with private reduced-rhs / solution / scratch vectors (work: [pairs][3][N]).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_differentiate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nparam,
-                                                                         const double *H, double *S)
+                                                                         const double *H, double *S, double *work)
 {
-    KERNEL_PROLOGUE
-    kkt_entries(ctx, P, I);
-    ldl_factor(ctx, P, I.panels, I.D, I.Dinv, KSrc{I.Wv, I.Gr, I.Cv, I.kx}, I.Lcsr, I.istat, I.prof);
-    for (int i = 0; i < nparam; i++) {
-        const double *rhs = H + ((long long)b * nparam + i) * P.total;
-        double *out = S + ((long long)b * nparam + i) * P.total;
-        direction_symmetric(ctx, P, I, rhs, out);
-        PAR_FOR(k, P.total) out[k] = -1.0 * out[k];
-        ctx.sync();
-    }
-    PROF_FLUSH(I.prof);
+    CTX_SETUP
+    const int pair = blockIdx.x;
+    if (pair >= B.count * nparam) return;
+    const int b = pair / nparam;
+    Inst I = B.inst(P, b);
+    I.rs = work + (long long)pair * 3 * P.N;
+    I.xs = I.rs + P.N;
+    I.xp = I.xs + P.N;
+    I.istat = nullptr;                       // (the per-instance counters are not shared between the CTAs of an instance)
+    I.prof = nullptr;
+    const double *rhs = H + (long long)pair * P.total;
+    double *out = S + (long long)pair * P.total;
+    reduced_rhs(ctx, P, I, rhs, I.rs);
+    ldl_solve(ctx, P, I.panels, I.D, I.Dinv, I.kx, I.Lcsr, I.rs, I.xs, I.xp, nullptr, nullptr);
+    recover_step(ctx, P, I, rhs, I.xs, out);
+    PAR_FOR(k, P.total) out[k] = -1.0 * out[k];
 }
 
 // evaluate!'s cache scatter: grid = (chunks of the pattern, instances); coalesced index reads and value
@@ -820,19 +828,27 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
     if (nparam <= 0) return 0;
     FRESH_VALUES();
     CUDA_OK(cudaSetDevice(h->device));
-    const size_t bytes = sizeof(double) * (size_t)h->batch * (size_t)nparam * (size_t)h->P.total;
-    double *dH = nullptr, *dS = nullptr;
+    const size_t pairs = (size_t)h->batch * (size_t)nparam;
+    const size_t bytes = sizeof(double) * pairs * (size_t)h->P.total, wbytes = sizeof(double) * pairs * 3 * (size_t)h->P.N;
+    double *dH = nullptr, *dS = nullptr, *dW = nullptr;
     CUDA_OK(cudaMalloc(&dH, bytes));
-    if (cudaMalloc(&dS, bytes) != cudaSuccess) { cudaFree(dH); return fail("cb200_differentiate: device allocation failed"); }
+    if (cudaMalloc(&dS, bytes) != cudaSuccess || cudaMalloc(&dW, wbytes) != cudaSuccess) {
+        cudaFree(dH); cudaFree(dS);
+        return fail("cb200_differentiate: device allocation failed");
+    }
     int rc = 0;
     do {
         if (cudaMemcpyAsync(dH, H_host, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = fail("H2D failed"); break; }
-        if (h->wide) {
+        if (cb200_kkt_factor_solve(h, 0)) { rc = -1; break; }          // assemble + factor at the current point and regularisation
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const bool wide = pairs <= (size_t)sms || h->sym().ctas_per_sm == 1;
+        if (wide) {
             if (cudaFuncSetAttribute(k_differentiate<CB_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
-            k_differentiate<CB_THREADS_WIDE><<<h->batch, CB_THREADS_WIDE, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS);
+            k_differentiate<CB_THREADS_WIDE><<<(unsigned)pairs, CB_THREADS_WIDE, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS, dW);
         } else {
             if (cudaFuncSetAttribute(k_differentiate<CB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
-            k_differentiate<CB_THREADS><<<h->batch, CB_THREADS, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS);
+            k_differentiate<CB_THREADS><<<(unsigned)pairs, CB_THREADS, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS, dW);
         }
         if (cudaGetLastError() != cudaSuccess) { rc = fail("k_differentiate launch failed"); break; }
         if (cudaMemcpyAsync(S_host, dS, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = fail("D2H failed"); break; }
@@ -841,6 +857,7 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
     } while (0);
     cudaFree(dH);
     cudaFree(dS);
+    cudaFree(dW);
     return rc;
 }
 

@@ -64,7 +64,9 @@ struct Batch {
     }
 };
 
+#ifndef CB_THREADS
 #define CB_THREADS 256
+#endif
 #define CB_THREADS_WIDE 512
 #define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
 #define CTX_SETUP                                                                                          \

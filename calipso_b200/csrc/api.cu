@@ -69,6 +69,9 @@ struct Batch {
 #endif
 #define CB_THREADS_WIDE 512
 #define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
+#define CB_THREADS_NARROW 192   // the four-CTA plan (symbolic.cpp, analyze_auto): 4 x 192 threads, the same 85-register cap
+// resident CTAs the heavy kernels are compiled for, by threads per CTA
+#define CB_CTAS_FOR(T) ((T) == CB_THREADS ? CB_MIN_CTAS : ((T) == CB_THREADS_NARROW ? 4 : 1))
 #define CTX_SETUP                                                                                          \
     if (threadIdx.x < 32) cb_prof[threadIdx.x] = 0;                                                        \
     {                                                                                                      \
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_residual(const __gr
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_search_direction(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
+__global__ void __launch_bounds__(THREADS, CB_CTAS_FOR(THREADS)) k_search_direction(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o)
 {
     KERNEL_PROLOGUE
     int st = search_direction(ctx, P, I, o);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_MIN_CTAS) k_lq_begin(const __gr
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o, int iterations)
+__global__ void __launch_bounds__(THREADS, CB_CTAS_FOR(THREADS)) k_lq_step(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, Options o, int iterations)
 {
     CTX_SETUP
     if ((int)blockIdx.x >= B.count) return;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS :
 // LinearSolver seam: factor the generic matrix / solve in place.  These two are the "KKT LDL^T solve" whose HBM
 // roofline bench.py reports (B_unit).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_ldl_factor(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int assemble_generic)
+__global__ void __launch_bounds__(THREADS, CB_CTAS_FOR(THREADS)) k_ldl_factor(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int assemble_generic)
 {
     CTX_SETUP
     const int b = blockIdx.x;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS :
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
+__global__ void __launch_bounds__(THREADS, CB_CTAS_FOR(THREADS)) k_ldl_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B)
 {
     CTX_SETUP
     const int b = blockIdx.x;
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS :
 
 // KKT path: assemble + factor with the current regularisation (no inertia loop) -- used by the roofline bench
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_kkt_factor_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nsolves)
+__global__ void __launch_bounds__(THREADS, CB_CTAS_FOR(THREADS)) k_kkt_factor_solve(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nsolves)
 {
     KERNEL_PROLOGUE
     ProfTimer pt{I.prof, 0};
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS :
 // parameter) pair gets its own CTA -- a single problem with many parameters fills the GPU instead of running its columns
 // one after the other on one SM -- with private reduced-rhs / solution / scratch vectors (work: [pairs][3][N]).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == CB_THREADS ? CB_MIN_CTAS : 1) k_differentiate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nparam,
+__global__ void __launch_bounds__(THREADS, CB_CTAS_FOR(THREADS)) k_differentiate(const __grid_constant__ DevProblem P, const __grid_constant__ Batch B, int nparam,
                                                                          const double *H, double *S, double *work)
 {
     CTX_SETUP
@@ -558,7 +561,7 @@ extern "C" int cb200_path_info(const cb200_handle *h, long long *out)
     const Symbolic &S = h->sym();
     out[0] = S.solve_smem; out[1] = S.ctas_per_sm; out[2] = (long long)S.scratch_doubles * 8; out[3] = S.n_cta_tasks;
     out[4] = S.n_generic_cta_tasks; out[5] = (long long)S.big.size() <= CB_MAX_CHAIN; out[6] = (long long)S.phases.size() <= CB_MAX_PHASES;
-    out[7] = h->wide ? CB_THREADS_WIDE : CB_THREADS;
+    out[7] = h->wide ? CB_THREADS_WIDE : h->sym().threads;
     return 0;
 }
 
@@ -729,6 +732,7 @@ extern "C" int cb200_set_options(cb200_handle *h, const cb200_options *o)
     do {                                                                                                  \
         CUDA_OK(cudaSetDevice(h->device));                                                                \
         if (h->wide) LAUNCH_SMEM_T(kernel, CB_THREADS_WIDE, __VA_ARGS__);                                 \
+        else if (h->sym().threads == CB_THREADS_NARROW) LAUNCH_SMEM_T(kernel, CB_THREADS_NARROW, __VA_ARGS__); \
         else LAUNCH_SMEM_T(kernel, CB_THREADS, __VA_ARGS__);                                              \
         CUDA_OK(cudaGetLastError());                                                                      \
     } while (0)
@@ -848,6 +852,9 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
         if (wide) {
             if (cudaFuncSetAttribute(k_differentiate<CB_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
             k_differentiate<CB_THREADS_WIDE><<<(unsigned)pairs, CB_THREADS_WIDE, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS, dW);
+        } else if (h->sym().threads == CB_THREADS_NARROW) {
+            if (cudaFuncSetAttribute(k_differentiate<CB_THREADS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            k_differentiate<CB_THREADS_NARROW><<<(unsigned)pairs, CB_THREADS_NARROW, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS, dW);
         } else {
             if (cudaFuncSetAttribute(k_differentiate<CB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
             k_differentiate<CB_THREADS><<<(unsigned)pairs, CB_THREADS, h->smem_bytes, h->stream>>>(h->P, h->B, nparam, dH, dS, dW);

@@ -85,6 +85,7 @@ struct DevProblem {   // everything shared by the instances of a batch (device p
     long long kx_total;
     const int *big_seq, *big_seq_bwd;          // shared-memory supernodes in forward / backward schedule order
     int nbig, max_sb_doubles, solve_smem;
+    int nleaf;                                 // > 0: the first nleaf permuted columns are the singleton leaves and the shared-memory solve keeps x[nleaf .. N) only
     const FwdEntry *pfwd;                      // per-phase bulk pulls into the pivot columns of the shared-memory supernodes
     const int *prow, *pphase_ptr;
     int max_big_nR;
@@ -1425,22 +1426,29 @@ __device__ __forceinline__ void chain_run_backward(const DevProblem &P, PartStre
 
 __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P, const double *__restrict__ pan,
                                             const double *D, const double *__restrict__ Dinv,
-                                            const double *__restrict__ Lcsr, const double *b, double *x,
+                                            const double *__restrict__ Lcsr, const double *b, double *x, double *xg,
                                             int *istat, long long *prof)
 {
     ProfTimer pt{prof, 0}, ps{prof, 0};
     pt.start();
     ps.start();
-    const int N = P.N, Npad = (N + 1) & ~1;
+    // With the leaves-first ordering (P.nleaf > 0) only x[nleaf .. N) lives in shared memory: a singleton leaf is final from
+    // the start in the forward sweep (y_leaf = b_leaf, read from the global scratch xg) and is written straight to the
+    // result in the backward sweep.  xs is biased so that xs[k] addresses column k for k >= nleaf.
+    const int N = P.N, nl = P.nleaf, Npad = (N - nl + 1) & ~1;
     const int tid = threadIdx.x, nthr = blockDim.x, wid = tid >> 5, nw = nthr >> 5;
-    double *xs = cb_dyn_smem;
+    double *xs = cb_dyn_smem - nl;
     const int buf_off = Npad, buf_len = P.max_sb_doubles;      // slot s at cb_dyn_smem + buf_off + s * buf_len
     double *yv = cb_dyn_smem + buf_off + 2 * buf_len;            // (named from cb_dyn_smem so that accesses stay LDS/STS)
     double *zero_cell = yv + 64;
     double *xr = yv + 80;                                         // x[R] of the current chain supernode (backward)
     const int leader = 32;
     if (tid == 0) *zero_cell = 0.0;
-    for (int k = tid; k < N; k += nthr) xs[k] = b[P.perm[k]];
+    for (int k = tid; k < N; k += nthr) {
+        const double v = b[P.perm[k]];
+        if (k >= nl) xs[k] = v; else xg[k] = v;
+    }
+    const double *__restrict__ xleaf = nl > 0 ? xg : xs;         // where the forward pass finds y_leaf
     // the mbarriers live for the whole kernel: continue the use numbering where the previous solve stopped
     PartStream st{pan, P.parts_fwd, P.nparts_fwd, 0, 0, cb_bar_uses, buf_off, buf_len};
     __syncthreads();
@@ -1470,7 +1478,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                 }
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (cidx[u] >= 0) acc += l[u] * xs[cidx[u]];
+                    if (cidx[u] >= 0) acc += l[u] * xleaf[cidx[u]];
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -1546,7 +1554,7 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
             __syncthreads();
         }
     }
-    for (int k = tid; k < N; k += nthr) xs[k] *= Dinv[k];
+    for (int k = nl + tid; k < N; k += nthr) xs[k] *= Dinv[k];
     __syncthreads();
     pt.stop(PROF_SOLVE_FWD);
     ps.stop(PROF_SF_PUSH);                                        // (counter: D^-1 scaling and bulk pulls after the last phase)
@@ -1620,14 +1628,17 @@ __device__ __noinline__ void ldl_solve_smem(const Ctx &ctx, const DevProblem &P,
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                if (sub == 0 && q < cnt) xs[li.x] -= acc;
+                if (sub == 0 && q < cnt) {
+                    if (nl > 0) x[P.perm[li.x]] = xg[li.x] * Dinv[li.x] - acc;      // straight to the result
+                    else xs[li.x] -= acc;
+                }
                 li = lin;
             }
             __syncthreads();
             ps.stop(PROF_SB_LEAVES);
         }
     }
-    for (int k = tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
+    for (int k = nl + tid; k < N; k += nthr) x[P.perm[k]] = xs[k];
     if (tid == 0 && istat) istat[I_SOLVES]++;
     __syncthreads();
     if (tid == 0) cb_bar_uses = st.base + (unsigned)st.nparts;
@@ -1646,7 +1657,7 @@ CB_DEVN void ldl_solve(const Ctx &ctx, const DevProblem &P, const double *pan, c
 {
 #if CB_ON_DEVICE
     if (P.solve_smem && ctx.scratch && blockDim.x >= 128) {
-        ldl_solve_smem(ctx, P, pan, D, Dinv, Lcsr, b, x, istat, prof);
+        ldl_solve_smem(ctx, P, pan, D, Dinv, Lcsr, b, x, xp, istat, prof);
         return;
     }
 #endif

@@ -171,7 +171,7 @@ template <class Up> void fill_symbolic(DevProblem &P, const Symbolic &S, Up up)
     P.dg_dst = up(S.dg_dst); P.dg_ptr = up(S.dg_ptr); P.dg_src = up(S.dg_src); P.dg_piv = up(S.dg_piv);
     P.kx_total = S.kx_total;
     P.big_seq = up(S.big_seq); P.big_seq_bwd = up(S.big_seq_bwd); P.nbig = (int)S.big_seq.size(); P.max_sb_doubles = S.max_sb_doubles;
-    P.solve_smem = S.solve_smem;
+    P.solve_smem = S.solve_smem; P.nleaf = S.leaves_first ? S.nleaf : 0;
     P.pfwd = up(S.pfwd); P.prow = up(S.prow); P.pphase_ptr = up(S.pphase_ptr); P.max_big_nR = S.max_big_nR;
     P.parts_fwd = up(S.parts_fwd); P.parts_bwd = up(S.parts_bwd);
     P.nparts_fwd = (int)S.parts_fwd.size() / 2; P.nparts_bwd = (int)S.parts_bwd.size() / 2;

@@ -131,16 +131,32 @@ static void permuted_upper(int n, const int *Ap, const int *Ai, const std::vecto
 
 const char *Symbolic::analyze_auto(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold)
 {
-    // doubles of dynamic shared memory a CTA may plan with at 3 / 2 / 1 resident CTAs per SM: (233472 / c - 1 KB reserved
-    // - 4 KB static) / 8, the single-CTA figure capped by the 227 KB per-block limit
-    static const int budgets[3] = {9250, 13952, 28000};
+    // Plans, in order of preference: resident CTAs per SM, doubles of dynamic shared memory a CTA may plan with at that
+    // residency ((233472 / c - 1 KB reserved - 4 KB static) / 8; the single-CTA figure capped by the 227 KB per-block limit),
+    // supernode width cap, panel size above which the solves stream a chain panel in two column parts, threads per CTA.
+    // Measured on B200 (profiles/r2_threads_per_cta_experiment.txt): the CTAs are bound by their own dependent chains, so
+    // more, narrower CTAs per SM win as long as the whole numeric path stays on the shared-memory code.
+    struct Plan { int ctas, budget, width, split, threads; bool leaves_first; };
+    // (Plan 0 -- four CTAs of 192 threads -- is kept for experiments, CB200_PLAN=0: measured on B200 it delivers what three
+    // CTAs of 256 threads deliver, because throughput follows the number of resident warps, 24 per SM either way at the
+    // 80-register cap, not the number of resident instances; profiles/r2_threads_per_cta_experiment.txt.)
+    static const Plan plans[] = {{4, 6656, 48, 2048, 192, true},  {3, 9250, 48, 2048, 256, false}, {3, 9250, 48, 2048, 256, true},
+                                 {2, 13952, 48, 2048, 256, false}, {2, 13952, 48, 2048, 256, true}, {1, 28000, 48, 2048, 512, false},
+                                 {1, 28000, 48, 2048, 512, true}};
+    const int nplans = (int)(sizeof(plans) / sizeof(plans[0]));
+    int first = 1;                                      // default: start at the three-CTA plan with x[N] resident
+    if (const char *e = getenv("CB200_PLAN")) first = std::max(0, std::min(nplans - 1, atoi(e)));
     const char *msg = "";
-    for (int k = 0; k < 3; k++) {
-        msg = analyze(n, Ap, Ai, user_perm, big_task_threshold, budgets[k]);
+    for (int k = first; k < nplans; k++) {
+        width_cap = plans[k].width;
+        part_split = plans[k].split;
+        leaves_first = plans[k].leaves_first;
+        msg = analyze(n, Ap, Ai, user_perm, big_task_threshold, plans[k].budget);
         if (msg[0]) return msg;
-        ctas_per_sm = 3 - k;
-        smem_budget = budgets[k];
-        if (n_cta_tasks == 0 || (solve_smem && n_generic_cta_tasks == 0)) break;
+        ctas_per_sm = plans[k].ctas;
+        smem_budget = plans[k].budget;
+        threads = plans[k].threads;
+        if (n_cta_tasks == 0 || (solve_smem && n_generic_cta_tasks == 0) || getenv("CB200_PLAN_ONLY")) break;
     }
     return msg;
 }
@@ -207,6 +223,25 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
     for (int k = 0; k < n; k++) iperm[perm[k]] = k;
     permuted_upper(n, Ap, Ai, iperm, Up, Ui);
     nnzL = etree_counts(n, Up, Ui, etree, Lnz);
+    nleaf = 0;
+    if (leaves_first) {
+        // a column is a singleton leaf iff it has no child in the elimination tree and does not start a multi-column
+        // fundamental supernode (step 4 below); moving those columns to the front keeps children before parents
+        std::vector<char> has_child(n, 0), leaf(n, 0);
+        for (int j = 0; j < n; j++)
+            if (etree[j] >= 0) has_child[etree[j]] = 1;
+        for (int j = 0; j < n; j++)
+            leaf[j] = !has_child[j] && !(j + 1 < n && etree[j] == j + 1 && Lnz[j] == Lnz[j + 1] + 1);
+        std::vector<int> p2;
+        p2.reserve(n);
+        for (int j = 0; j < n; j++) if (leaf[j]) p2.push_back(perm[j]);
+        nleaf = (int)p2.size();
+        for (int j = 0; j < n; j++) if (!leaf[j]) p2.push_back(perm[j]);
+        perm.swap(p2);
+        for (int k = 0; k < n; k++) iperm[perm[k]] = k;
+        permuted_upper(n, Ap, Ai, iperm, Up, Ui);
+        nnzL = etree_counts(n, Up, Ui, etree, Lnz);
+    }
     flops = 0;
     for (int j = 0; j < n; j++) flops += (long long)Lnz[j] * Lnz[j];
     // 3. column structures of L: struct(j) = lower(A)_j U (struct(children) \ {j})
@@ -247,7 +282,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         }
     }
     // 4. fundamental supernodes (consecutive columns, parent = next column, nested structure) ...
-    const int max_width = 48;    // keeps (rows + width) x width panels inside the shared-memory budget
+    const int max_width = width_cap;    // keeps (rows + width) x width panels inside the shared-memory budget
     std::vector<int> fstart;
     for (int j = 0; j < n; j++) {
         bool merge = j > 0 && etree[j - 1] == j && Lnz[j - 1] == Lnz[j] + 1 && (j - fstart.back()) < max_width;
@@ -434,7 +469,7 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
             bt.panel_doubles = (int)(panel_off[t + 1] - panel_off[t]);
             bt.asm_begin = bt.asm_end = 0;
             bt.h1 = w;
-            if (bt.panel_doubles > 2048 && w >= 4) bt.h1 = ((w + 1) / 2 + 1) & ~1;   // even => both parts 16-byte aligned
+            if (bt.panel_doubles > part_split && w >= 4) bt.h1 = ((w + 1) / 2 + 1) & ~1;   // even => both parts 16-byte aligned
             int col = 0;
             YChunk ch{0, 0, (int)ystage_src.size(), 0, (int)ypiv.size(), 0, 0, (int)ymask.size()};
             ymask.resize(ymask.size() + ntI, 0u);
@@ -540,7 +575,14 @@ const char *Symbolic::analyze(int n, const int *Ap, const int *Ai, const int *us
         int max_nR_big = 0;
         for (int t = 0; t < ns; t++)
             if (big_index[t] >= 0) max_nR_big = std::max(max_nR_big, rows_ptr[t + 1] - rows_ptr[t]);
-        long long need = (((long long)N + 1) & ~1LL) + 2LL * max_sb_doubles + 64 + 16 + ((max_nR_big + 1) & ~1);
+        if (leaves_first) {      // the leading columns must be exactly the singleton-leaf supernodes of the schedule
+            int cnt = 0;
+            bool ok = true;
+            for (int t = 0; t < ns; t++)
+                if (cls[t] == 0) { cnt++; ok = ok && sn_start[t] < nleaf; }
+            if (!ok || cnt != nleaf) return "internal error: leaves-first ordering does not match the leaf classification";
+        }
+        long long need = (((long long)(N - nleaf) + 1) & ~1LL) + 2LL * max_sb_doubles + 64 + 16 + ((max_nR_big + 1) & ~1);
         solve_smem = (!big.empty() && need <= smem_budget_doubles) ? 1 : 0;
         if (solve_smem) scratch_doubles = (int)std::max<long long>(scratch_doubles, need);
         parts_fwd.clear(); parts_bwd.clear();

@@ -170,6 +170,13 @@ struct Symbolic {
     const char *analyze_auto(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold);
     int ctas_per_sm = 3;          // the occupancy the kept plan was sized for
     int smem_budget = 9250;       // ... and its budget in doubles
+    int threads = 256;            // ... and the threads per CTA of the heavy kernels that go with it
+    int width_cap = 48;           // widest supernode the analysis forms (panel (rows + width) x width must fit the budget)
+    int part_split = 2048;        // chain panels larger than this many doubles are streamed in two column parts
+    bool leaves_first = false;    // order every singleton leaf before every other column (same fill, still a topological order of
+                                  // the elimination tree): the solves then keep only x[nleaf .. N) in shared memory -- the leaves
+                                  // are final from the start (forward) and can be written straight to the result (backward)
+    int nleaf = 0;                // number of leading singleton-leaf columns when leaves_first (else 0)
     int n_cta_tasks = 0, n_generic_cta_tasks = 0;   // CTA-scope supernodes / those that fell back to the global-memory code
 };
 

@@ -197,12 +197,13 @@ def test_narrow_and_wide_kernel_instantiations_agree():
 
 def test_quadruped_shape_runs_on_the_shared_memory_path_and_matches_oracle():
     """A pattern beyond BASELINE's cfg3 -- the dimensions of the reference's quadruped example (N = 6987, stages of 75
-    variables, test/examples/quadruped_gait.jl:236-244,460-464): the shared-memory plan is re-sized (two resident CTAs per
-    SM), nothing falls back to the global-memory code, and the complete solve! agrees with the oracle."""
+    variables, test/examples/quadruped_gait.jl:236-244,460-464): the shared-memory plan is re-sized (leaves-first ordering:
+    only the non-leaf unknowns stay in shared memory during the solves, which keeps three resident CTAs per SM), nothing falls
+    back to the global-memory code, and the complete solve! agrees with the oracle."""
     Ps = [lqc.quadruped_shape(i) for i in range(3)]
     k = BatchKKT(Ps[0], batch=3, binding=backends.binding("cuda"))
     paths = k.paths()
-    assert paths["solve_in_shared_memory"] == 1 and paths["cta_supernodes_generic"] == 0 and paths["ctas_per_sm"] == 2
+    assert paths["solve_in_shared_memory"] == 1 and paths["cta_supernodes_generic"] == 0 and paths["ctas_per_sm"] == 3
     assert k.info()["N"] == 6987
     k.load_lq(Ps)
     k.initialize(np.stack([P.x0 for P in Ps]))

@@ -14,6 +14,8 @@ extern "C" int symstats(int n, int m, int p, int q_nn, int nsoc, const int *soc_
     printf("N %d nnzK %d nnzL %lld flops(sum Lnz^2) %lld ns %d levels %d phases %zu panel_total %lld kx_total %lld lcsr_total %lld scratch %d solve_smem %d nbig %zu\n",
            S.N, S.nnzA, S.nnzL, S.flops, S.ns, S.nlevels, S.phases.size(), S.panel_total, S.kx_total, S.lcsr_total,
            S.scratch_doubles, S.solve_smem, S.big.size());
+    printf("plan: ctas/SM %d budget %d threads %d width cap %d; cta tasks %d generic %d; chunks %zu; max_sb %d\n", S.ctas_per_sm, S.smem_budget, S.threads,
+           S.width_cap, S.n_cta_tasks, S.n_generic_cta_tasks, S.ychunks.size(), S.max_sb_doubles);
     long long leaf_cols = 0, leaf_rows = 0, big_cols = 0, small_cols = 0;
     std::map<int, int> leaf_hist;
     for (size_t pi = 0; pi < S.phases.size(); pi++) {

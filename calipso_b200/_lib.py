@@ -106,6 +106,9 @@ SYMBOLS = {
     "cb200_scatter_plan": (C.c_int, [vp, C.c_int, C.c_int, c_ip, c_ip, c_ip]),
     "cb200_scatter": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
     "cb200_scatter_buffer": (vp, [vp, C.c_int]),
+    "cb200_stage_plan": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_ip]),
+    "cb200_stage_scatter": (C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int]),
+    "cb200_stage_buffer": (vp, [vp, C.c_int]),
     "cb200_lq_evaluate": (C.c_int, [vp, C.c_int, C.c_int]),
     "cb200_lq_begin": (C.c_int, [vp, C.c_int]),
     "cb200_lq_step": (C.c_int, [vp, C.c_int]),

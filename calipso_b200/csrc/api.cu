@@ -68,10 +68,17 @@ struct Batch {
 #define CB_THREADS 256
 #endif
 #define CB_THREADS_WIDE 512
+#ifndef CB_MIN_CTAS
 #define CB_MIN_CTAS 3   // registers capped at 85 per thread: three CTAs per SM
+#endif
+#ifndef CB_THREADS_NARROW
 #define CB_THREADS_NARROW 192   // the four-CTA plan (symbolic.cpp, analyze_auto): 4 x 192 threads, the same 85-register cap
+#endif
+#ifndef CB_NARROW_CTAS
+#define CB_NARROW_CTAS 4
+#endif
 // resident CTAs the heavy kernels are compiled for, by threads per CTA
-#define CB_CTAS_FOR(T) ((T) == CB_THREADS ? CB_MIN_CTAS : ((T) == CB_THREADS_NARROW ? 4 : 1))
+#define CB_CTAS_FOR(T) ((T) == CB_THREADS ? CB_MIN_CTAS : ((T) == CB_THREADS_NARROW ? CB_NARROW_CTAS : 1))
 #define CTX_SETUP                                                                                          \
     if (threadIdx.x < 32) cb_prof[threadIdx.x] = 0;                                                        \
     {                                                                                                      \
@@ -290,6 +297,18 @@ __global__ void __launch_bounds__(256) k_scatter(int nnz, int ncaches, const int
                    gridDim.x * blockDim.x);
 }
 
+// stage-level scatter of the trajectory-optimisation front end: grid = (chunks of the output, instances);
+// coalesced writes, gathered cache reads in program order
+__global__ void __launch_bounds__(256) k_stage_gather(int nout, int accumulate, const int *__restrict__ ptr, const int *__restrict__ src,
+                                                      const double *__restrict__ caches, long long cache_total,
+                                                      double *__restrict__ out, long long out_len, int first_instance)
+{
+    Ctx ctx{(int)threadIdx.x, (int)blockDim.x, 0, nullptr, nullptr, nullptr, nullptr};
+    const long long b = first_instance + blockIdx.y;
+    stage_gather(ctx, nout, accumulate, ptr, src, caches + b * cache_total, out + b * out_len, blockIdx.x * blockDim.x,
+                 gridDim.x * blockDim.x);
+}
+
 __global__ void k_count_states(Batch B, long long *counts)
 {
     __shared__ int c[4];
@@ -341,6 +360,7 @@ struct cb200_handle {
     int nnzW = 0, nnzG = 0, nnzC = 0;
     bool wide = false;          // heavy kernels with CB_THREADS_WIDE threads per instance (small batches)
     struct Scatter { ScatterPlan plan; const int *d_idx = nullptr; double *d_caches = nullptr; } scatter[3];   // W, G, C
+    struct Stage { StagePlan plan; const int *d_ptr = nullptr, *d_src = nullptr; double *d_caches = nullptr; } stage[5];   // grad f, (g'y)_x, (h'z)_x, g, h
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
     int *d_order = nullptr;     // cb200_lq_set_order
     double *d_cand = nullptr;   // cb200_filter_search: candidates' callback outputs
@@ -931,6 +951,68 @@ extern "C" int cb200_scatter(cb200_handle *h, int which, const double *caches_ho
         }
     }
     if (which == CB200_W_VALUES || which == CB200_G_VALUES) h->values_dirty = true;
+    return 0;
+}
+
+static int stage_slot(int which)
+{
+    return which == CB200_GRADIENT ? 0 : which == CB200_EQ_DUAL_GRAD ? 1 : which == CB200_CONE_DUAL_GRAD ? 2
+         : which == CB200_EQUALITY ? 3 : which == CB200_CONE ? 4 : -1;
+}
+
+extern "C" int cb200_stage_plan(cb200_handle *h, int which, int accumulate, int count, const int *dst)
+{
+    NEED_KKT();
+    const int slot = stage_slot(which);
+    if (slot < 0) return fail("cb200_stage_plan: which must be CB200_GRADIENT, CB200_EQ_DUAL_GRAD, CB200_CONE_DUAL_GRAD, CB200_EQUALITY or CB200_CONE");
+    if (count > 0 && !dst) return fail("cb200_stage_plan: no index list");
+    cb200_handle::Stage &sg = h->stage[slot];
+    std::string err = sg.plan.build((int)h->arr[which].len, accumulate != 0, count, dst);
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));      // a previous plan may still be in use
+    for (void *old : {(void *)sg.d_ptr, (void *)sg.d_src, (void *)sg.d_caches})      // a new plan replaces the previous one
+        if (old) {
+            h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), old), h->allocs.end());
+            cudaFree(old);
+        }
+    sg.d_ptr = sg.d_src = nullptr;
+    sg.d_caches = nullptr;
+    if (!err.empty()) { sg.plan = StagePlan(); return fail(err); }
+    bool ok = true;
+    sg.d_ptr = upload(h, sg.plan.ptr, ok);
+    sg.d_src = upload(h, sg.plan.src, ok);
+    sg.d_caches = dalloc(h, sg.plan.cache_total, ok, false);
+    if (!ok) return fail("cb200_stage_plan: device allocation failed");
+    return 0;
+}
+
+extern "C" void *cb200_stage_buffer(cb200_handle *h, int which)
+{
+    const int slot = stage_slot(which);
+    return slot < 0 ? nullptr : (void *)h->stage[slot].d_caches;
+}
+
+extern "C" int cb200_stage_scatter(cb200_handle *h, int which, const double *caches_host, int first, int count)
+{
+    NEED_KKT();
+    const int slot = stage_slot(which);
+    if (slot < 0 || !h->stage[slot].d_ptr) return fail("cb200_stage_scatter: no stage plan for this array");
+    if (check_array(h, which, first, count)) return -1;
+    if (count == 0) return 0;
+    const cb200_handle::Stage &sg = h->stage[slot];
+    const ArrayDesc &a = h->arr[which];
+    CUDA_OK(cudaSetDevice(h->device));
+    if (caches_host && sg.plan.cache_total > 0)
+        CUDA_OK(cudaMemcpyAsync(sg.d_caches + (long long)first * sg.plan.cache_total, caches_host,
+                                sizeof(double) * sg.plan.cache_total * count, cudaMemcpyHostToDevice, h->stream));
+    if (sg.plan.nout > 0) {
+        const int chunks = std::max(1, std::min((sg.plan.nout + 1023) / 1024, 64));
+        for (int c0 = 0; c0 < count; c0 += 65535) {       // gridDim.y limit
+            k_stage_gather<<<dim3(chunks, std::min(count - c0, 65535)), 256, 0, h->stream>>>(
+                sg.plan.nout, sg.plan.accumulate, sg.d_ptr, sg.d_src, sg.d_caches, sg.plan.cache_total, a.ptr, a.len, first + c0);
+            CUDA_OK(cudaGetLastError());
+        }
+    }
     return 0;
 }
 

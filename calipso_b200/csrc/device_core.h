@@ -462,6 +462,26 @@ CB_DEV void scatter_caches(const Ctx &ctx, int nnz, int ncaches, const int *__re
     }
 }
 
+// Stage-level scatter of the trajectory-optimisation front end as a gather (plan: host_setup.h StagePlan): output entry i
+// receives, after fill!(out, 0.0), the entries src[ptr[i] .. ptr[i + 1]) of the concatenated per-stage caches in program order
+// -- added one by one (`gradient[idx...] += cache[i]`, trajectory_optimization/dynamics.jl:172-179, constraints.jl:203-212,
+// `gradient[indices[t]] .+= cache`, costs.jl:115-120) or only the last of them (`violations[indices[t]] .= cache`,
+// dynamics.jl:143-148, constraints.jl:169-176).
+CB_DEV void stage_gather(const Ctx &ctx, int nout, int accumulate, const int *__restrict__ ptr, const int *__restrict__ src,
+                         const double *__restrict__ cache, double *__restrict__ out, int first, int stride)
+{
+    for (int i = first + ctx.tid; i < nout; i += stride) {
+        const int k0 = ptr[i], k1 = ptr[i + 1];
+        double v = 0.0;
+        if (accumulate) {
+            for (int k = k0; k < k1; k++) v += cache[src[k]];
+        } else if (k1 > k0) {
+            v = cache[src[k1 - 1]];
+        }
+        out[i] = v;
+    }
+}
+
 // The entries of the reduced matrix K that are not plain copies of W, G, C values:
 // kx = [W diagonal + eps_p | y diagonal | nonnegative z diagonal | upper triangles of the second-order z blocks].
 // eps_p, eps_d, rho enter exactly where residual_jacobian_variables.jl:83-105,131,143-164 puts them.  The matrix itself

@@ -225,6 +225,30 @@ struct ScatterPlan {
     }
 };
 
+// cb200_stage_plan: the index list of a stage-level scatter (dst[k] = output entry that concatenated cache entry k goes to,
+// in the reference's program order) turned into per-output gather lists that keep that order.
+struct StagePlan {
+    int nout = 0, accumulate = 0;
+    long long cache_total = 0;
+    std::vector<int> ptr, src;     // [nout + 1], [cache_total]
+
+    std::string build(int nout_, int accumulate_, int count, const int *dst)
+    {
+        if (count < 0) return "stage plan: negative length";
+        nout = nout_; accumulate = accumulate_; cache_total = count;
+        ptr.assign((size_t)nout + 1, 0);
+        for (int k = 0; k < count; k++) {
+            if (dst[k] < 0 || dst[k] >= nout) return "stage plan: index out of range";
+            ptr[(size_t)dst[k] + 1]++;
+        }
+        for (int i = 0; i < nout; i++) ptr[(size_t)i + 1] += ptr[(size_t)i];
+        src.assign((size_t)count, 0);
+        std::vector<int> next(ptr.begin(), ptr.end() - 1);
+        for (int k = 0; k < count; k++) src[(size_t)next[(size_t)dst[k]]++] = k;      // ascending k within an output: program order
+        return "";
+    }
+};
+
 template <class Up> void fill_problem(DevProblem &P, const HostProblem &H, Up up)
 {
     P.n = H.n; P.m = H.m; P.p = H.p; P.total = H.total; P.q_nn = H.q_nn; P.nsoc = H.nsoc; P.tri_total = H.tri_total;

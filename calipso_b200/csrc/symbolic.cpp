@@ -156,6 +156,7 @@ const char *Symbolic::analyze_auto(int n, const int *Ap, const int *Ai, const in
         ctas_per_sm = plans[k].ctas;
         smem_budget = plans[k].budget;
         threads = plans[k].threads;
+        if (const char *e = getenv("CB200_PLAN_THREADS")) threads = atoi(e);      // tuning experiments (tools/)
         if (n_cta_tasks == 0 || (solve_smem && n_generic_cta_tasks == 0) || getenv("CB200_PLAN_ONLY")) break;
     }
     return msg;

@@ -254,6 +254,26 @@ class BatchKKT:
         self.b.check(self.lib.cb200_scatter(self.h, A[name], dp(v) if L > 0 else None, first, v.shape[0]))
         self.b.check(self.lib.cb200_synchronize(self.h))   # the source buffer may be a temporary
 
+    def stage_plan(self, name, indices, accumulate):
+        """The gather plan of a stage-level scatter of the trajectory-optimisation front end (cb200_stage_plan;
+        trajectory_optimization/evaluate.jl:15-28,77-136,206-241,297-327).  name: "GRADIENT", "EQ_DUAL_GRAD", "CONE_DUAL_GRAD"
+        (accumulate=True: `gradient[idx] += cache[i]`) or "EQUALITY", "CONE" (accumulate=False: `violations[idx] .= cache`).
+        indices: the stages' 0-based index lists in program order (a list of lists, or one flat list)."""
+        flat = [np.asarray(ix, dtype=np.int64).ravel() for ix in indices] if len(indices) and np.ndim(indices[0]) > 0 else \
+            [np.asarray(indices, dtype=np.int64).ravel()]
+        dst = i32(np.concatenate(flat)) if flat else i32([])
+        self.b.check(self.lib.cb200_stage_plan(self.h, A[name], int(bool(accumulate)), len(dst), ip(dst) if len(dst) else None))
+        self._stage_len = getattr(self, "_stage_len", {})
+        self._stage_len[name] = len(dst)
+
+    def stage_scatter(self, name, caches, first=0):
+        """Scatter the concatenated stage caches ([count, plan length]) into the vector `name` of instances
+        first .. first+count-1."""
+        L = self._stage_len[name]
+        v = f64(caches).reshape(-1, L) if L > 0 else np.zeros((np.shape(caches)[0] if np.ndim(caches) > 1 else 1, 0))
+        self.b.check(self.lib.cb200_stage_scatter(self.h, A[name], dp(v) if L > 0 else None, first, v.shape[0]))
+        self.b.check(self.lib.cb200_synchronize(self.h))   # the source buffer may be a temporary
+
     def jacobian_times(self, v):
         v = f64(v).reshape(self.batch, self.total)
         out = np.zeros_like(v)

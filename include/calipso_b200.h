@@ -221,6 +221,29 @@ int cb200_differentiate(cb200_handle *h, int num_parameters, const double *jacob
 int cb200_scatter_plan(cb200_handle *h, int which, int ncaches, const int *cache_len, const int *rows, const int *cols);
 int cb200_scatter(cb200_handle *h, int which, const double *caches_host, int first_instance, int count);
 void *cb200_scatter_buffer(cb200_handle *h, int which);
+/* Stage-level scatter of the trajectory-optimisation front end (SURVEY.md section 8(f) row N2 proper): the callbacks the
+ * front end hands to the solver (trajectory_optimization/methods.jl:2-44) clear a vector of the problem data and then loop
+ * over the stages, each stage evaluating its generated function into a small cache and writing the cache through an index
+ * list:
+ *   accumulate = 1   `gradient[indices[t]] .+= cache` / `gradient[idx...] += cache[i]` -- objective gradient
+ *                    (evaluate.jl:15-28, costs.jl:115-120), (g'y)_x (evaluate.jl:206-241, dynamics.jl:172-179,
+ *                    constraints.jl:203-212) and (h'z)_x (evaluate.jl:297-327): neighbouring stages overlap (dynamics t
+ *                    and t+1 both touch x_{t+1}), the sums are formed in program order: dynamics, stage constraints,
+ *                    general constraints, each stage by stage;
+ *   accumulate = 0   `violations[indices[t]] .= cache` -- g(x) (evaluate.jl:77-109, dynamics.jl:143-148,
+ *                    constraints.jl:169-176) and h(x) (evaluate.jl:111-136): the last write to an entry wins.
+ * Entries no stage writes are 0.0 (the fill!).  cb200_stage_plan takes the concatenation of the stages' index lists in that
+ * program order (dst[k], 0-based, = the entry of `which` that entry k of the concatenated caches goes to) and turns it into
+ * per-entry gather lists that keep the order, so the result is bit-identical to the reference's loops.  which =
+ * CB200_GRADIENT, CB200_EQ_DUAL_GRAD, CB200_CONE_DUAL_GRAD (accumulate = 1) or CB200_EQUALITY, CB200_CONE (accumulate = 0).
+ * cb200_stage_scatter copies caches_host ([count][length], instance-major; NULL = the caller already wrote the device buffer
+ * cb200_stage_buffer(h, which), laid out [batch][length]) and fills `which` for instances first .. first+count-1 on the
+ * handle's stream (asynchronous).  The flat second-derivative and Jacobian caches of the same callbacks
+ * (`jacobians[sparsity + count] = v`, dynamics.jl:150-170,181-205, constraints.jl:178-201,214-239) are plain concatenations of
+ * the stage caches: they go through cb200_scatter unchanged. */
+int cb200_stage_plan(cb200_handle *h, int which, int accumulate, int length, const int *dst);
+int cb200_stage_scatter(cb200_handle *h, int which, const double *caches_host, int first_instance, int count);
+void *cb200_stage_buffer(cb200_handle *h, int which);
 /* out = J v for instance-major v (mul! with jacobian_variables, iterative_refinement.jl:9) -- tests / glue */
 int cb200_jacobian_times(cb200_handle *h, const double *v_host, double *out_host);
 

@@ -213,9 +213,20 @@ end
 scatter!(s::B200Newton, which::Cint, caches::Vector{Float64}) = GC.@preserve caches check(ccall((:cb200_scatter, LIBCB200), Cint,
     (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cint), s.handle, which, caches, 0, 1))
 
+# the front end's stage loops (trajectory_optimization/evaluate.jl:15-28,77-136,206-241,297-327) on the device: `indices` = the
+# stages' (1-based) index lists in program order, accumulate = true for `gradient[idx...] += cache[i]`, false for
+# `violations[indices[t]] .= cache`; `caches` = the stage caches concatenated in the same order
+function stage_plan!(s::B200Newton, which::Cint, indices::Vector{Vector{Int}}, accumulate::Bool)
+    dst = Cint[i - 1 for v in indices for i in v]
+    check(ccall((:cb200_stage_plan, LIBCB200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}),
+                s.handle, which, accumulate ? 1 : 0, length(dst), dst))
+end
+stage_scatter!(s::B200Newton, which::Cint, caches::Vector{Float64}) = GC.@preserve caches check(ccall((:cb200_stage_scatter, LIBCB200), Cint,
+    (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cint), s.handle, which, caches, 0, 1))
+
 synchronize(s::B200Newton) = check(ccall((:cb200_synchronize, LIBCB200), Cint, (Ptr{Cvoid},), s.handle))
 
 export B200LDLSolver, b200_ldl_solver, b200_amd, factorize!, compute_inertia!, linear_solve!, B200Newton, initialize!, cone!,
-       residual!, search_direction!, cone_search!, apply_step!, differentiate!, scatter_plan!, scatter!
+       residual!, search_direction!, cone_search!, apply_step!, differentiate!, scatter_plan!, scatter!, stage_plan!, stage_scatter!
 
 end # module

@@ -483,6 +483,21 @@ def scatter_dense(shape, sparsity, cache):
     return M
 
 
+def stage_scatter(n_out, indices, caches, accumulate):
+    """The stage loops of the trajectory-optimisation front end, restated literally: `fill!(out, 0.0)` (evaluate.jl:16,78,112,
+    207,298), then stage by stage in program order either `out[idx...] += cache[i]` (constraint_dual_jacobian_variables!,
+    dynamics.jl:172-179, constraints.jl:203-212; gradient_variables!, costs.jl:115-120) or `out[indices[t]] .= cache`
+    (constraints!, dynamics.jl:143-148, constraints.jl:169-176).  indices / caches: per-stage lists (0-based indices)."""
+    out = np.zeros(n_out)
+    for idx, cache in zip(indices, caches):
+        for i, j in enumerate(idx):
+            if accumulate:
+                out[j] += cache[i]
+            else:
+                out[j] = cache[i]
+    return out
+
+
 def lagrangian_hessian_dense(n, sparsities, caches):
     """residual_jacobian_variables.jl:9-15: H[i, j] = objective_xx[i, j]; H[i, j] += equality_dual_xx[i, j];
     H[i, j] += cone_dual_xx[i, j] on the dense matrices scatter_dense produced (missing caches count as zero matrices)."""

@@ -30,6 +30,7 @@ struct cb200_handle {
     long long ksize = 0;
     const Symbolic &sym() const { return generic ? gsym : hp.sym; }
     struct Scatter { ScatterPlan plan; std::vector<double> caches; bool set = false; } scatter[3];
+    struct Stage { StagePlan plan; std::vector<double> caches; bool set = false; } stage[5];
 };
 
 enum { X_ERR = CB200_NUM_ARRAYS, X_CORR, X_TMP, X_DINV, X_XP, X_FILTER, X_KRYLOV, X_KX, X_LCSR, X_WF, X_GR, X_COUNT };
@@ -366,6 +367,43 @@ extern "C" int cb200_scatter(cb200_handle *h, int which, const double *caches_ho
     for (int b = first; b < first + count; b++)
         scatter_caches(ctx, sc.plan.nnz, sc.plan.ncaches, sc.plan.idx.data(), sc.caches.data() + b * L,
                        h->arr[which].data() + (long long)b * h->len[which], 0, 1);
+    return 0;
+}
+static int stage_slot(int which)
+{
+    return which == CB200_GRADIENT ? 0 : which == CB200_EQ_DUAL_GRAD ? 1 : which == CB200_CONE_DUAL_GRAD ? 2
+         : which == CB200_EQUALITY ? 3 : which == CB200_CONE ? 4 : -1;
+}
+extern "C" int cb200_stage_plan(cb200_handle *h, int which, int accumulate, int count, const int *dst)
+{
+    if (h->generic) return fail("not available on a LinearSolver-seam handle");
+    const int slot = stage_slot(which);
+    if (slot < 0) return fail("cb200_stage_plan: which must be CB200_GRADIENT, CB200_EQ_DUAL_GRAD, CB200_CONE_DUAL_GRAD, CB200_EQUALITY or CB200_CONE");
+    if (count > 0 && !dst) return fail("cb200_stage_plan: no index list");
+    auto &sg = h->stage[slot];
+    std::string err = sg.plan.build((int)h->len[which], accumulate != 0, count, dst);
+    if (!err.empty()) { sg.plan = StagePlan(); sg.set = false; return fail(err); }
+    sg.caches.assign((size_t)std::max<long long>(sg.plan.cache_total * h->batch, 1), 0.0);
+    sg.set = true;
+    return 0;
+}
+extern "C" void *cb200_stage_buffer(cb200_handle *h, int which)
+{
+    const int slot = stage_slot(which);
+    return slot < 0 || !h->stage[slot].set ? nullptr : (void *)h->stage[slot].caches.data();
+}
+extern "C" int cb200_stage_scatter(cb200_handle *h, int which, const double *caches_host, int first, int count)
+{
+    const int slot = stage_slot(which);
+    if (h->generic || slot < 0 || !h->stage[slot].set) return fail("cb200_stage_scatter: no stage plan for this array");
+    if (check(h, which, first, count)) return -1;
+    auto &sg = h->stage[slot];
+    const long long L = sg.plan.cache_total;
+    if (caches_host && L > 0) memcpy(sg.caches.data() + first * L, caches_host, sizeof(double) * L * count);
+    Ctx ctx{0, 1, 0, g_red, h->scratch.data(), nullptr, nullptr};
+    for (int b = first; b < first + count; b++)
+        stage_gather(ctx, sg.plan.nout, sg.plan.accumulate, sg.plan.ptr.data(), sg.plan.src.data(), sg.caches.data() + b * L,
+                     h->arr[which].data() + (long long)b * h->len[which], 0, 1);
     return 0;
 }
 extern "C" int cb200_jacobian_times(cb200_handle *h, const double *v, double *out)

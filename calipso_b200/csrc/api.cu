@@ -1059,9 +1059,13 @@ extern "C" int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, l
         done += chunk;
         if (cb200_allreduce_counts(h, c)) { h->wide = wide0; return -1; }
         if (c[0] == 0) break;
-        // the tail of a batched solve: once the instances still running (converged ones exit at once) fit one CTA per
-        // SM, the 512-thread instantiations finish their iterations sooner
-        if (!getenv("CB200_THREADS") && c[0] <= (long long)sms * h->nranks) h->wide = true;
+        // The tail of a batched solve: once the instances still running (converged ones exit at once) fit one CTA per SM, the
+        // 512-thread instantiations can take over.  Opt-in (CB200_TAIL_WIDE=1): the reductions of a 512-thread CTA associate
+        // differently, so an instance's iterates would depend on when the switch happens (batch, check interval, ranks), and
+        // measured on B200 it buys little -- the late iterations of the hard instances that form the tail are dominated by
+        // refinement solves, 1.35x faster at 512 threads (profiles/r2_tail_experiments.txt).
+        static const bool tail_wide = getenv("CB200_TAIL_WIDE") && atoi(getenv("CB200_TAIL_WIDE")) != 0;
+        if (tail_wide && !getenv("CB200_THREADS") && c[0] <= (long long)sms * h->nranks) h->wide = true;
     }
     h->wide = wide0;
     if (counts) for (int k = 0; k < 4; k++) counts[k] = c[k];

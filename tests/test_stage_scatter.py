@@ -167,3 +167,46 @@ def test_errors(backend):
     k._stage_len = {"CONE": 0}
     with pytest.raises(_lib.CalipsoB200Error):
         k.stage_scatter("CONE", np.zeros((2, 0)))                       # no plan for this array
+
+
+@pytest.mark.parametrize("backend", backends.BACKENDS)
+def test_pendulum_solve_with_device_stage_loops(backend):
+    """BASELINE cfg1 solved with the front end's stage loops on the device: the callbacks only fill the stage caches
+    (what the generated functions do), cb200_stage_scatter forms grad f, g(x) and (g'y)_x.  Same Newton iterations as the
+    flat callbacks, same solution (the sums differ from J' y in the last bits only)."""
+    from calipso_b200.solver import Solver, initialize, solve
+    T = 11
+    P = problems.pendulum(0, T)
+    b = backends.binding(backend)
+    kd = BatchKKT(P, batch=1, binding=b)                  # the handle whose vectors the stage loops fill
+    xu, xuy = trajopt_indices(T, 2, 1)
+    g_idx = [[2 * t, 2 * t + 1] for t in range(T - 1)] + [[2 * (T - 1), 2 * (T - 1) + 1], [2 * (T - 1) + 2, 2 * (T - 1) + 3]]
+    d_idx = xuy + [xu[0], xu[T - 1]]
+    kd.stage_plan("EQUALITY", g_idx, accumulate=False)
+    kd.stage_plan("EQ_DUAL_GRAD", d_idx, accumulate=True)
+    kd.stage_plan("GRADIENT", xu, accumulate=True)
+    calls = [0]
+
+    def staged(flags, x, y, z, out):
+        P.callback(flags & ~(2 | 4 | 16), x, y, z, out)            # objective value, Hessian and Jacobian caches as before
+        if flags & (2 | 4 | 16):
+            dyn_g, dyn_dual, eq_g, eq_dual, cost_grad = pendulum_stage_caches(P, T, x, y)
+            if flags & 2:
+                kd.stage_scatter("GRADIENT", np.concatenate(cost_grad)[None])
+                out.gradient[:] = kd.get("GRADIENT")[0]
+            if flags & 4:
+                kd.stage_scatter("EQUALITY", np.concatenate(dyn_g + eq_g)[None])
+                out.equality[:] = kd.get("EQUALITY")[0]
+            if flags & 16:
+                kd.stage_scatter("EQ_DUAL_GRAD", np.concatenate(dyn_dual + eq_dual)[None])
+                out.eq_dual_grad[:] = kd.get("EQ_DUAL_GRAD")[0]
+            calls[0] += 1
+
+    s = Solver(P, staged, binding=b)
+    initialize(s, P.x0)
+    assert solve(s) is True
+    ref = Solver(P, P.callback, binding=b)
+    initialize(ref, P.x0)
+    assert solve(ref) is True
+    assert calls[0] > 0 and s.iterations == ref.iterations
+    assert np.abs(s.solution - ref.solution).max() / (1.0 + np.abs(ref.solution).max()) < 1e-9

@@ -364,6 +364,8 @@ struct cb200_handle {
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
     int *d_order = nullptr;     // cb200_lq_set_order
     double *d_cand = nullptr;   // cb200_filter_search: candidates' callback outputs
+    double *d_diff = nullptr;   // cb200_differentiate: right-hand sides, results, solve scratch
+    size_t diff_bytes = 0;
     size_t cand_bytes = 0;
 };
 
@@ -856,12 +858,24 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
     CUDA_OK(cudaSetDevice(h->device));
     const size_t pairs = (size_t)h->batch * (size_t)nparam;
     const size_t bytes = sizeof(double) * pairs * (size_t)h->P.total, wbytes = sizeof(double) * pairs * 3 * (size_t)h->P.N;
-    double *dH = nullptr, *dS = nullptr, *dW = nullptr;
-    CUDA_OK(cudaMalloc(&dH, bytes));
-    if (cudaMalloc(&dS, bytes) != cudaSuccess || cudaMalloc(&dW, wbytes) != cudaSuccess) {
-        cudaFree(dH); cudaFree(dS);
-        return fail("cb200_differentiate: device allocation failed");
+    // work area (right-hand sides, results, per-column solve scratch): kept with the handle and grown on demand -- a
+    // cudaMalloc / cudaFree pair per call costs more than the solves (5-400 ms measured, tools/r2_diff_probe.py)
+    const size_t need = 2 * bytes + wbytes;
+    if (need > h->diff_bytes) {
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        if (h->d_diff) {
+            h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void *)h->d_diff), h->allocs.end());
+            cudaFree(h->d_diff);
+            h->d_diff = nullptr;
+            h->diff_bytes = 0;
+        }
+        void *d = nullptr;
+        if (cudaMalloc(&d, need) != cudaSuccess) return fail("cb200_differentiate: device allocation failed");
+        h->allocs.push_back(d);
+        h->d_diff = (double *)d;
+        h->diff_bytes = need;
     }
+    double *dH = h->d_diff, *dS = dH + pairs * (size_t)h->P.total, *dW = dS + pairs * (size_t)h->P.total;
     int rc = 0;
     do {
         if (cudaMemcpyAsync(dH, H_host, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = fail("H2D failed"); break; }
@@ -884,9 +898,6 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { rc = fail(std::string("cb200_differentiate: ") + cudaGetErrorString(e)); break; }
     } while (0);
-    cudaFree(dH);
-    cudaFree(dS);
-    cudaFree(dW);
     return rc;
 }
 

@@ -35,6 +35,15 @@ P0 = Ps[0]
 keysW = [(int(r), int(c)) for c in range(P0.n) for r in P0.W_rowval[P0.W_colptr[c]:P0.W_colptr[c + 1]]]
 k.scatter_plan("W_VALUES", [keysW])
 k.scatter("W_VALUES", np.stack([P.W_val for P in plist]))      # k_scatter
+# the front end's stage loops: (g'y)_x through overlapping (x_t, u_t, x_{t+1}) index lists      k_stage_gather
+T, nx, nu = 40, 36, 12
+xuy = [list(range(t * (nx + nu), t * (nx + nu) + nx + nu + nx)) for t in range(T - 1)]
+k.stage_plan("EQ_DUAL_GRAD", xuy, accumulate=True)
+k.stage_scatter("EQ_DUAL_GRAD", np.random.default_rng(1).standard_normal((B, sum(len(i) for i in xuy))))
+# filter line search over a block of 4 candidates (callback outputs uploaded)                   k_filter_reset, k_filter_search
+k.filter_reset()
+rng = np.random.default_rng(2)
+k.filter_search(0, rng.standard_normal((B, 4)), rng.standard_normal((B, 4, k.m)), np.abs(rng.standard_normal((B, 4, k.p))) + 1.0)
 k.synchronize()
 # LinearSolver seam on a cfg3-shaped quasi-definite matrix: k_ldl_factor, k_ldl_solve
 n, m, p = P0.n, P0.m, P0.p

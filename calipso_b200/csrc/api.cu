@@ -366,6 +366,8 @@ struct cb200_handle {
     double *d_cand = nullptr;   // cb200_filter_search: candidates' callback outputs
     double *d_diff = nullptr;   // cb200_differentiate: right-hand sides, results, solve scratch
     size_t diff_bytes = 0;
+    cudaStream_t copy_stream = nullptr;   // cb200_differentiate: the upload of the right-hand sides runs beside the factorisation
+    cudaEvent_t copy_done = nullptr;
     size_t cand_bytes = 0;
 };
 
@@ -564,6 +566,8 @@ extern "C" void cb200_destroy(cb200_handle *h)
     for (void *p : h->allocs) cudaFree(p);
     if (h->d_counts) cudaFree(h->d_counts);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->copy_done) cudaEventDestroy(h->copy_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -878,8 +882,15 @@ extern "C" int cb200_differentiate(cb200_handle *h, int nparam, const double *H_
     double *dH = h->d_diff, *dS = dH + pairs * (size_t)h->P.total, *dW = dS + pairs * (size_t)h->P.total;
     int rc = 0;
     do {
-        if (cudaMemcpyAsync(dH, H_host, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = fail("H2D failed"); break; }
+        // the right-hand sides are uploaded on a second stream while the factorisation (which does not read them) runs
+        if (!h->copy_stream && (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                                cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming) != cudaSuccess)) { rc = fail("stream creation failed"); break; }
+        if (cudaEventRecord(h->copy_done, h->stream) != cudaSuccess ||                      // (the work area may still be in use)
+            cudaStreamWaitEvent(h->copy_stream, h->copy_done, 0) != cudaSuccess ||
+            cudaMemcpyAsync(dH, H_host, bytes, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess ||
+            cudaEventRecord(h->copy_done, h->copy_stream) != cudaSuccess) { rc = fail("H2D failed"); break; }
         if (cb200_kkt_factor_solve(h, 0)) { rc = -1; break; }          // assemble + factor at the current point and regularisation
+        if (cudaStreamWaitEvent(h->stream, h->copy_done, 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const bool wide = pairs <= (size_t)sms || h->sym().ctas_per_sm == 1;

@@ -919,6 +919,9 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
         }
         if (ng > 0) ctx.sync();
     }
+#ifdef CB_PROF_PANEL_SPLIT
+    pt.stop(PROF_SPARE0);
+#endif
     double *dd = Y + 72;                 // w pivots
 #if CB_ON_DEVICE
     if (nrow <= (int)blockDim.x) {
@@ -929,6 +932,10 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
         PAR_FOR(k, w) dd[k] = S[k + (long long)k * ldp];
         ctx.sync();
     }
+#ifdef CB_PROF_PANEL_SPLIT
+    __syncthreads();
+    pt.stop(PROF_FACTOR_BIG_PANEL);
+#endif
     // write back the factor panel; the diagonal and the upper triangle of the pivot block are stored as zeros so
     // that the triangular sweeps of the solves need no predicates
     for (int k = wid; k < w; k += nw) {
@@ -950,7 +957,11 @@ CB_DEV void factor_supernode_big(const Ctx &ctx, const DevProblem &P, double *pa
         Dinv[c0 + k] = dk != 0.0 ? 1.0 / dk : 0.0;
     }
     ctx.sync();
+#ifdef CB_PROF_PANEL_SPLIT
+    pt.stop(PROF_SPARE1);
+#else
     pt.stop(PROF_FACTOR_BIG_PANEL);
+#endif
 }
 
 #if CB_ON_DEVICE

@@ -328,7 +328,7 @@ class BatchKKT:
         o = i32(order) if order is not None else None
         self.b.check(self.lib.cb200_lq_set_order(self.h, ip(o) if o is not None else None))
 
-    def lq_solve(self, max_steps=1100, check_every=4):
+    def lq_solve(self, max_steps=1100, check_every=32):
         counts = np.zeros(4, dtype=np.int64)
         steps = C.c_int(0)
         self.b.check(self.lib.cb200_lq_solve(self.h, max_steps, check_every, counts.ctypes.data_as(_lib.c_llp),

@@ -276,7 +276,11 @@ int cb200_filter_search(cb200_handle *h, int first, int count, const double *f_h
  * wave of a batched solve. */
 int cb200_lq_set_order(cb200_handle *h, const int *order);
 /* run until every instance converged / gave up or max_steps passes; with an NCCL communicator attached the
- * termination test is the all-reduced count over ranks.  counts[4] = running, converged, gave up, error (global). */
+ * termination test is the all-reduced count over ranks.  counts[4] = running, converged, gave up, error (global).
+ * check_every = Newton iterations an instance may run inside one launch before the host looks at the counters (32-byte
+ * read-back + the all-reduce): every instance leaves its launch as soon as it has converged, so a large value costs
+ * nothing but the granularity of max_steps; small values put a host synchronisation into the loop (measured on B200:
+ * 290 / 282 / 280 ms per batched solve for 4 / 8 / until convergence, profiles/r1_lq_schedule_ab.txt). */
 int cb200_lq_solve(cb200_handle *h, int max_steps, int check_every, long long *counts, int *steps_done);
 
 /* ------------------------------------------------------------------------------------------------ LinearSolver seam

@@ -528,8 +528,10 @@ def run_gpu(args):
     # (rank 0) configs[3] = ONE instance on one B200
     literal = {}
 
-    def small_batch(bb, first_seed):
-        Pl = [lqc.cfg3(first_seed + i) for i in range(bb)]
+    def small_batch(bb, first_seed, make=lqc.cfg3, distinct=None):
+        nd = min(bb, distinct or bb)
+        Pd_ = [make(first_seed + i) for i in range(nd)]
+        Pl = [Pd_[i % nd] for i in range(bb)]
         kk = BatchKKT(Pl[0], batch=bb, device=local)
         kk.load_lq(Pl)
         x0 = np.stack([P.x0 for P in Pl])
@@ -548,6 +550,8 @@ def run_gpu(args):
         kk.set_scalars(eps_p=1e-7, eps_d=1e-7)
         kk.kkt_factor_solve(1)
         ms_unit = timed(lambda: kk.kkt_factor_solve(1), 10, st2)
+        small_batch.paths = kk.paths()
+        small_batch.info = kk.info()
         kk.close()
         return its, ms, ms_unit
 
@@ -557,6 +561,15 @@ def run_gpu(args):
         literal["cfg4_8_instances_per_gpu"] = dict(instances_per_gpu=8, instances=8 * world, newton_it_per_s=tot8 / (ms8 * 1e-3),
                                                    ms_per_solve=ms8, newton_iterations=tot8, kkt_factor_solve_ms=unit8,
                                                    what="BASELINE.json configs[4]: seeds 8*rank .. 8*rank+7 per GPU, max over ranks")
+        # the quadruped shape SURVEY.md cites (test/examples/quadruped_gait.jl: N_sym = 6954, 76-variable stages; here N = 6987,
+        # 75-variable stages): the leaves-first shared-memory plan keeps three resident CTAs per SM; one wave of 444
+        itsq, msq, unitq = small_batch(444, 8 * rank, make=lqc.quadruped_shape, distinct=8)
+        totq = rank_sum(itsq)
+        literal["quadruped_shape_batch"] = dict(instances_per_gpu=444, N=int(small_batch.info["N"]), nnz_L=int(small_batch.info["nnzL"]),
+                                                newton_it_per_s=totq / (msq * 1e-3), ms_per_solve=msq, newton_iterations=totq,
+                                                kkt_factor_solve_ms=unitq, code_paths=small_batch.paths,
+                                                what="complete solve! of 444 quadruped-shaped instances per GPU (8 distinct seeds); "
+                                                     "kkt_factor_solve_ms = one launch of the KKT-solve unit over the batch")
         # configs[3]: one instance; every rank runs it (the timing helper contains collectives), rank 0's number is reported
         its1, ms1, unit1 = small_batch(1, 0)
         literal["cfg3_single_instance"] = dict(batch=1, newton_it_per_s=its1 / (ms1 * 1e-3), ms_per_solve=ms1,

@@ -359,6 +359,7 @@ struct cb200_handle {
     int nranks = 1;
     int nnzW = 0, nnzG = 0, nnzC = 0;
     bool wide = false;          // heavy kernels with CB_THREADS_WIDE threads per instance (small batches)
+    int resident_ctas = 0;      // CTAs of the heavy kernels that actually fit an SM (occupancy query at creation)
     struct Scatter { ScatterPlan plan; const int *d_idx = nullptr; double *d_caches = nullptr; } scatter[3];   // W, G, C
     struct Stage { StagePlan plan; const int *d_ptr = nullptr, *d_src = nullptr; double *d_caches = nullptr; } stage[5];   // grad f, (g'y)_x, (h'z)_x, g, h
     bool values_dirty = true;   // W or G values changed since the row-ordered copies were refreshed
@@ -450,6 +451,21 @@ static bool finish_batch(cb200_handle *h)
     }
     h->B.scratch_doubles = h->sym().scratch_doubles;
     h->smem_bytes = (size_t)h->B.scratch_doubles * sizeof(double);
+    if (!h->wide) {   // what the hardware grants at this shared-memory size (a plan that overshoots its budget would silently lose a CTA per SM)
+        int n = 0;
+        const int T = h->sym().threads;
+        auto query = [&](auto kernel) {
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 0;
+            if ((size_t)fa.maxDynamicSharedSizeBytes < h->smem_bytes &&
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) return 0;
+            int k = 0;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kernel, T, h->smem_bytes) == cudaSuccess ? k : 0;
+        };
+        n = T == CB_THREADS_NARROW ? query(k_kkt_factor_solve<CB_THREADS_NARROW>) : query(k_kkt_factor_solve<CB_THREADS>);
+        if (n == 0) cudaGetLastError();
+        h->resident_ctas = n;
+    }
     return true;
 }   // multiply-adds above which a supernode gets the whole CTA
 
@@ -585,7 +601,7 @@ extern "C" int cb200_info(const cb200_handle *h, long long *out)
 extern "C" int cb200_path_info(const cb200_handle *h, long long *out)
 {
     const Symbolic &S = h->sym();
-    out[0] = S.solve_smem; out[1] = S.ctas_per_sm; out[2] = (long long)S.scratch_doubles * 8; out[3] = S.n_cta_tasks;
+    out[0] = S.solve_smem; out[1] = (h->resident_ctas > 0 && h->resident_ctas < S.ctas_per_sm) ? h->resident_ctas : S.ctas_per_sm; out[2] = (long long)S.scratch_doubles * 8; out[3] = S.n_cta_tasks;
     out[4] = S.n_generic_cta_tasks; out[5] = (long long)S.big.size() <= CB_MAX_CHAIN; out[6] = (long long)S.phases.size() <= CB_MAX_PHASES;
     out[7] = h->wide ? CB_THREADS_WIDE : h->sym().threads;
     return 0;

@@ -140,7 +140,9 @@ const char *Symbolic::analyze_auto(int n, const int *Ap, const int *Ai, const in
     // (Plan 0 -- four CTAs of 192 threads -- is kept for experiments, CB200_PLAN=0: measured on B200 it delivers what three
     // CTAs of 256 threads deliver, because throughput follows the number of resident warps, 24 per SM either way at the
     // 80-register cap, not the number of resident instances; profiles/r2_threads_per_cta_experiment.txt.)
-    static const Plan plans[] = {{4, 6656, 48, 2048, 192, true},  {3, 9250, 48, 2048, 256, false}, {3, 9250, 48, 2048, 256, true},
+    // (three CTAs: 233472 / 3 = 77824 bytes per CTA - 1024 reserved - 3968 static = 72832 bytes = 9104 doubles; a plan that
+    // asks for more silently runs at two CTAs per SM)
+    static const Plan plans[] = {{4, 6656, 48, 2048, 192, true},  {3, 9100, 48, 2048, 256, false}, {3, 9100, 48, 2048, 256, true},
                                  {2, 13952, 48, 2048, 256, false}, {2, 13952, 48, 2048, 256, true}, {1, 28000, 48, 2048, 512, false},
                                  {1, 28000, 48, 2048, 512, true}};
     const int nplans = (int)(sizeof(plans) / sizeof(plans[0]));

@@ -163,13 +163,13 @@ struct Symbolic {
     // still postordered (which does not change the fill) so that supernodes are contiguous.
     // Returns an empty string on success, else an error message.
     const char *analyze(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold,
-                        int smem_budget_doubles = 9250);   // 74 KB + 4 KB static + 1 KB reserved, three CTAs per SM
+                        int smem_budget_doubles = 9100);   // 72.8 KB + 4 KB static + 1 KB reserved, three CTAs per SM
     // The same with the shared-memory budget chosen for the pattern: the analysis is run for three, two and one resident
     // CTA per SM (228 KB of shared memory per SM on sm_100) and the first plan that keeps the whole numeric path on the
     // shared-memory code (solve with x[N] resident, every CTA-scope supernode staged) is kept; if none does, the last one.
     const char *analyze_auto(int n, const int *Ap, const int *Ai, const int *user_perm, int big_task_threshold);
     int ctas_per_sm = 3;          // the occupancy the kept plan was sized for
-    int smem_budget = 9250;       // ... and its budget in doubles
+    int smem_budget = 9100;       // ... and its budget in doubles
     int threads = 256;            // ... and the threads per CTA of the heavy kernels that go with it
     int width_cap = 48;           // widest supernode the analysis forms (panel (rows + width) x width must fit the budget)
     int part_split = 2048;        // chain panels larger than this many doubles are streamed in two column parts

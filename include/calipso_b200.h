@@ -133,7 +133,8 @@ void cb200_destroy(cb200_handle *h); /* Julia finalizer */
 int cb200_info(const cb200_handle *h, long long *out);
 /* Which code paths the handle's pattern selected (they differ in speed, not in results).  out[8]: 1 if the solves keep
  * x[N] in shared memory and stream the chain panels by TMA (else the global-memory solve); resident CTAs per SM the plan was
- * sized for (3, 2 or 1: chosen from N and the widest supernode against the 228 KB of shared memory of an SM); dynamic
+ * sized for (3, 2 or 1: chosen from N and the widest supernode against the 228 KB of shared memory of an SM; if the
+ * occupancy query at creation grants fewer than that, the granted number is reported instead); dynamic
  * shared memory per CTA in bytes; CTA-scope supernodes; those of them that do not fit the shared-memory staging and run
  * the global-memory code; 1 if the chain descriptors / the phase schedule are cached in shared memory (<= 64 chain supernodes,
  * <= 48 phases; otherwise they are read from global memory); threads per CTA of the heavy kernels (256 or 512). */
